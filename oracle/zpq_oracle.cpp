@@ -1,0 +1,1239 @@
+// zpq_oracle.cpp -- CPU ORACLE for the ZPAQ block codec path.  TEST INFRASTRUCTURE ONLY.
+//
+// This file restates, on the CPU and in plain C++17, the algorithm the reference
+// (mnadareski/ZPAQSharp, a C# transliteration of libzpaq 7.12) defines for the block
+// compress / decompress path.  It is the checker the CUDA product path is compared with and
+// the timed CPU baseline of bench.py.  Nothing in zpaqsharp_b200/ may include, link or call
+// it; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs use it.
+//
+// PARITY STATUS: "parity unpinned" for compressed bit streams.  The reference ships no
+// archive, no expected-output vector and cannot be compiled.  What IS
+// pinned against the reference's own literals (tests/golden/reference_kat.json, extracted by
+// tests/golden/make_golden.py): the state table, squash/stretch/dt/dt2k tables and their
+// checksums, the three built-in model bytecodes, compsize[], the locator tag and rolling-hash
+// constants, and the hand-checkable stored-mode framing.
+//
+// Each function cites the reference file:line (relative to /root/reference/ZPAQSharp) whose
+// behaviour it follows.  Where the C# text is known to be corrupt
+// the libzpaq 7.12 semantics documented in the comments / LICENSE text are followed instead
+// and the spot is marked "restored".
+//
+// Front-end split: method-string expansion, makeConfig and the ZPAQL assembler live in
+// oracle/frontend.py (string processing); this file takes the resulting header / PCOMP
+// bytecode and does all byte and bit work.
+
+#include <cstdint>
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <algorithm>
+#include <numeric>
+
+namespace orc {
+
+typedef uint8_t U8;
+typedef uint16_t U16;
+typedef uint32_t U32;
+typedef uint64_t U64;
+
+struct Error : std::runtime_error {
+  explicit Error(const char* m) : std::runtime_error(m) {}
+};
+[[noreturn]] static void fail(const char* m) { throw Error(m); }  // LibZPAQ.cs:22-24 error()
+
+// ---------------------------------------------------------------------------------------
+// Component descriptor sizes, Component.cs:27-43
+// ---------------------------------------------------------------------------------------
+enum { NONE = 0, CONS, CM, ICM, MATCH, AVG, MIX2, MIX, ISSE, SSE };
+static const int kCompSize[10] = {0, 2, 3, 2, 3, 4, 6, 6, 3, 5};
+static inline int compsize(int t) { return (t >= 0 && t < 10) ? kCompSize[t] : 0; }
+
+// ---------------------------------------------------------------------------------------
+// Model independent tables.  Predictor.cs:54-67 (construction), :1358,1394,1526,1699 (the
+// closed forms the literals were produced from), StateTable.cs:21-149 (ns literal; rebuilt
+// here from the bit-history automaton rules and checked against the literal by the tests).
+// ---------------------------------------------------------------------------------------
+struct Tables {
+  U16 squash[4096];
+  int16_t stretch[32768];
+  int dt[1024];
+  int dt2k[256];
+  U8 ns[1024];
+  Tables();
+};
+
+namespace statetable {
+// Bit-history states are (n0, n1, last-bit-variant).  A pair is representable when the larger
+// count is within a bound that shrinks as the smaller count grows.
+static int variants(int n0, int n1) {
+  static const int bound[6] = {20, 48, 15, 8, 6, 5};
+  if (n0 < n1) std::swap(n0, n1);
+  if (n1 < 0 || n1 >= 6 || n0 > bound[n1]) return 0;
+  return 1 + (n1 > 0 && n0 + n1 <= 17);
+}
+static int decay(int n) { return (n >= 1) + (n >= 2) + (n >= 3) + (n >= 4) + (n >= 5) + (n >= 7) + (n >= 8); }
+static void step(int& n0, int& n1, int y) {
+  if (n0 < n1) { step(n1, n0, 1 - y); return; }
+  if (y) { ++n1; n0 = decay(n0); } else { ++n0; n1 = decay(n1); }
+  while (!variants(n0, n1)) {
+    if (n1 < 2) --n0;
+    else { n0 = (n0 * (n1 - 1) + n1 / 2) / n1; --n1; }
+  }
+}
+static void build(U8* ns) {
+  const int N = 50;
+  static U8 id[N][N][2];
+  memset(id, 0, sizeof(id));
+  int next = 0;
+  for (int tot = 0; tot < N; ++tot)
+    for (int n1 = 0; n1 <= tot; ++n1) {
+      int n0 = tot - n1, v = variants(n0, n1);
+      if (v) { id[n0][n1][0] = (U8)next; id[n0][n1][1] = (U8)(next + v - 1); next += v; }
+    }
+  memset(ns, 0, 1024);
+  for (int n0 = 0; n0 < N; ++n0)
+    for (int n1 = 0; n1 < N; ++n1)
+      for (int y = 0; y < variants(n0, n1); ++y) {
+        int s = id[n0][n1][y], a = n0, b = n1;
+        step(a, b, 0); ns[s * 4 + 0] = id[a][b][0];
+        a = n0; b = n1;
+        step(a, b, 1); ns[s * 4 + 1] = id[a][b][1];
+        ns[s * 4 + 2] = (U8)n0; ns[s * 4 + 3] = (U8)n1;
+      }
+}
+}  // namespace statetable
+
+Tables::Tables() {
+  for (int i = 0; i < 4096; ++i) {  // Predictor.cs:54-58
+    if (i < 1376) squash[i] = 0;
+    else if (i >= 2720) squash[i] = 32767;
+    else squash[i] = (U16)(int)(32768.0 / (1 + std::exp((i - 2048) * (-1.0 / 64))));
+  }
+  for (int i = 0; i < 32768; ++i)  // Predictor.cs:60-67
+    stretch[i] = (int16_t)((int)(std::log((i + 0.5) / (32767.5 - i)) * 64 + 0.5 + 100000) - 100000);
+  for (int i = 0; i < 1024; ++i) dt[i] = (1 << 17) / (i * 2 + 3) * 2;  // Predictor.cs:1394
+  dt2k[0] = 0;
+  for (int i = 1; i < 256; ++i) dt2k[i] = 2048 / i;  // Predictor.cs:1358
+  statetable::build(ns);
+  U32 sq = 0, st = 0;  // Predictor.cs:69-78
+  for (int i = 32767; i >= 0; --i) st = st * 3 + (U32)(int)stretch[i];
+  for (int i = 4095; i >= 0; --i) sq = sq * 3 + squash[i];
+  if (st != 3887533746u || sq != 2278286169u) fail("oracle: squash/stretch table checksum mismatch");
+}
+static const Tables& T() { static Tables t; return t; }
+
+static inline int st_next(int s, int y) { return T().ns[s * 4 + y]; }  // StateTable.cs:151
+static inline int st_cminit(int s) {                                    // StateTable.cs:158-162
+  const U8* ns = T().ns;
+  return ((ns[s * 4 + 3] * 2 + 1) << 22) / (ns[s * 4 + 2] + ns[s * 4 + 3] + 1);
+}
+static inline int squash(int x) { return T().squash[x + 2048]; }  // Predictor.cs:496-501
+static inline int stretch(int x) { return T().stretch[x]; }       // Predictor.cs:504-509
+static inline int clamp2k(int x) { return x < -2048 ? -2048 : x > 2047 ? 2047 : x; }  // restored, SURVEY 8c
+static inline int clamp512k(int x) {                                                   // restored, SURVEY 8c
+  return x < -(1 << 19) ? -(1 << 19) : x >= (1 << 19) ? (1 << 19) - 1 : x;
+}
+
+// ---------------------------------------------------------------------------------------
+// SHA-1 (FIPS 180-4).  The reference calls a SHA1 class it does not contain
+// (LibZPAQ.cs:144-154, Compressor.cs:239-244); any conforming implementation is identical.
+// ---------------------------------------------------------------------------------------
+struct SHA1 {
+  U32 h[5]; U64 len; U8 buf[64]; int fill;
+  SHA1() { reset(); }
+  void reset() { h[0] = 0x67452301; h[1] = 0xEFCDAB89; h[2] = 0x98BADCFE; h[3] = 0x10325476; h[4] = 0xC3D2E1F0; len = 0; fill = 0; }
+  static U32 rol(U32 x, int n) { return (x << n) | (x >> (32 - n)); }
+  void block(const U8* p) {
+    U32 w[80];
+    for (int i = 0; i < 16; ++i) w[i] = (U32)p[4 * i] << 24 | (U32)p[4 * i + 1] << 16 | (U32)p[4 * i + 2] << 8 | p[4 * i + 3];
+    for (int i = 16; i < 80; ++i) w[i] = rol(w[i - 3] ^ w[i - 8] ^ w[i - 14] ^ w[i - 16], 1);
+    U32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+    for (int i = 0; i < 80; ++i) {
+      U32 f, k;
+      if (i < 20) { f = (b & c) | (~b & d); k = 0x5A827999; }
+      else if (i < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1; }
+      else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDC; }
+      else { f = b ^ c ^ d; k = 0xCA62C1D6; }
+      U32 t = rol(a, 5) + f + e + k + w[i];
+      e = d; d = c; c = rol(b, 30); b = a; a = t;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+  }
+  void put(int c) { buf[fill++] = (U8)c; ++len; if (fill == 64) { block(buf); fill = 0; } }
+  void write(const U8* p, size_t n) {
+    while (n && fill) { put(*p++); --n; }
+    while (n >= 64) { block(p); p += 64; n -= 64; len += 64; }
+    while (n) { put(*p++); --n; }
+  }
+  void result(U8 out[20]) {
+    U64 bits = len * 8;
+    put(0x80);
+    while (fill != 56) put(0);
+    for (int i = 7; i >= 0; --i) put((int)(bits >> (8 * i)) & 255);
+    for (int i = 0; i < 5; ++i) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
+    reset();
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Byte source / sink used by the framing code (Reader.cs:7-28, Writer.cs:12-29)
+// ---------------------------------------------------------------------------------------
+struct ByteSource {
+  const U8* p; size_t n, pos;
+  ByteSource(const U8* p_, size_t n_) : p(p_), n(n_), pos(0) {}
+  int get() { return pos < n ? p[pos++] : -1; }
+};
+typedef std::vector<U8> Bytes;
+
+// ---------------------------------------------------------------------------------------
+// ZPAQL virtual machine.  ZPAQL.cs:112-179 (read/write), :1010-1026 (init), :1028-1265
+// (execute/run0), ISA text :226-347.  The instruction set is decoded by field
+// (00dddxxx / 01dddsss / 1xxxxsss) rather than by a 256-way case list.
+// ---------------------------------------------------------------------------------------
+struct ZPAQL {
+  Bytes header;          // hsize[2] hh hm ph pm n COMP 0 (128 guard) HCOMP 0
+  int cend, hbegin, hend;
+  Bytes m; std::vector<U32> h; U32 r[256];
+  U32 a, b, c, d; int f, pc;
+  Bytes* output; SHA1* sha1;  // OUT destination (ZPAQL.cs:186-207; outc/flush restored)
+  ZPAQL() : output(nullptr), sha1(nullptr) { clear(); }
+  void clear() { cend = hbegin = hend = 0; a = b = c = d = 0; f = pc = 0; header.clear(); h.clear(); m.clear(); }
+
+  // ZPAQL.cs:112-156
+  int read(ByteSource& in) {
+    int lo = in.get(), hi = in.get();
+    if (lo < 0 || hi < 0) fail("unexpected end of file");
+    int hsize = lo + hi * 256;
+    header.assign(hsize + 300, 0);
+    cend = hbegin = hend = 0;
+    header[cend++] = hsize & 255;
+    header[cend++] = hsize >> 8;
+    while (cend < 7) header[cend++] = (U8)in.get();
+    int n = header[cend - 1];
+    for (int i = 0; i < n; ++i) {
+      int type = in.get();
+      if (type < 0 || type > 255) fail("unexpected end of file");
+      header[cend++] = (U8)type;
+      int size = compsize(type);
+      if (size < 1) fail("Invalid component type");
+      if (cend + size > hsize) fail("COMP overflows header");
+      for (int j = 1; j < size; ++j) header[cend++] = (U8)in.get();
+    }
+    if ((header[cend++] = (U8)in.get()) != 0) fail("missing COMP END");
+    hbegin = hend = cend + 128;
+    if (hend > hsize + 129) fail("missing HCOMP");
+    while (hend < hsize + 129) {
+      int op = in.get();
+      if (op == -1) fail("unexpected end of file");
+      header[hend++] = (U8)op;
+    }
+    if ((header[hend++] = (U8)in.get()) != 0) fail("missing HCOMP END");
+    return cend + hend - hbegin;
+  }
+  // ZPAQL.cs:158-179
+  bool write(Bytes& out, bool pp) const {
+    if (header.size() <= 6) return false;
+    if (!pp) out.insert(out.end(), header.begin(), header.begin() + cend);
+    else { out.push_back((hend - hbegin) & 255); out.push_back((hend - hbegin) >> 8); }
+    out.insert(out.end(), header.begin() + hbegin, header.begin() + hend);
+    return true;
+  }
+  // ZPAQL.cs:1010-1026 via inith()/initp() :45-56
+  void init(int hbits, int mbits) {
+    if (hbits > 32) fail("H too big");
+    if (mbits > 32) fail("M too big");
+    if (hbits > 30 || mbits > 32) fail("oracle: H/M larger than this host allows");
+    h.assign((size_t)1 << hbits, 0);
+    m.assign((size_t)1 << mbits, 0);
+    memset(r, 0, sizeof(r));
+    a = b = c = d = 0; pc = 0; f = 0;
+  }
+  void inith() { init(header[2], header[3]); }
+  void initp() { init(header[4], header[5]); }
+  // ZPAQL.cs:58-81
+  double memory() const {
+    auto p2 = [](int x) { return std::ldexp(1.0, x); };
+    double mem = p2(header[2] + 2) + p2(header[3]) + p2(header[4] + 2) + p2(header[5]) + (double)header.size();
+    int cp = 7;
+    for (int i = 0; i < header[6]; ++i) {
+      double size = p2(header[cp + 1]);
+      switch (header[cp]) {
+        case CM: mem += 4 * size; break;
+        case ICM: mem += 64 * size + 1024; break;
+        case MATCH: mem += 4 * size + p2(header[cp + 2]); break;
+        case MIX2: mem += 2 * size; break;
+        case MIX: mem += 4 * size * header[cp + 3]; break;
+        case ISSE: mem += 64 * size + 2048; break;
+        case SSE: mem += 128 * size; break;
+      }
+      cp += compsize(header[cp]);
+    }
+    return mem;
+  }
+
+  U8& M(U32 i) { return m[i & (m.size() - 1)]; }
+  U32& H(U32 i) { return h[i & (h.size() - 1)]; }
+  void outc(int ch) {  // restored, SURVEY appendix B
+    if (output) output->push_back((U8)ch);
+    if (sha1) sha1->put(ch);
+  }
+  void flush() {}
+
+  // ZPAQL.cs:1253-1265
+  void run(U32 input) {
+    pc = hbegin; a = input;
+    while (execute()) {}
+  }
+  // operand fetch for source field sss (ZPAQL.cs:256-266)
+  U32 src(int s) {
+    switch (s) {
+      case 0: return a; case 1: return b; case 2: return c; case 3: return d;
+      case 4: return M(b); case 5: return M(c); case 6: return H(d);
+      default: return header[pc++];
+    }
+  }
+  void store(int dst, U32 v) {
+    switch (dst) {
+      case 0: a = v; break; case 1: b = v; break; case 2: c = v; break; case 3: d = v; break;
+      case 4: M(b) = (U8)v; break; case 5: M(c) = (U8)v; break; case 6: H(d) = v; break;
+    }
+  }
+  U32 load(int dst) {
+    switch (dst) {
+      case 0: return a; case 1: return b; case 2: return c; case 3: return d;
+      case 4: return M(b); case 5: return M(c); default: return H(d);
+    }
+  }
+  // ZPAQL.cs:1028-1251
+  int execute() {
+    if (pc < 0 || pc >= (int)header.size()) fail("ZPAQL execution error");
+    int op = header[pc++];
+    if (op < 64) {
+      int ddd = op >> 3, x = op & 7;
+      if (ddd == 7) {  // 00111xxx specials
+        switch (x) {
+          case 0: return 0;                                   // HALT
+          case 1: outc(a & 255); break;                       // OUT
+          case 3: a = (a + M(b) + 512) * 773; break;          // HASH
+          case 4: H(d) = (H(d) + a + 512) * 773; break;       // HASHD
+          case 7: pc += ((header[pc] + 128) & 255) - 127; break;  // JMP
+          default: fail("ZPAQL execution error");
+        }
+        return 1;
+      }
+      switch (x) {
+        case 0:  // ddd<>a ; opcode 0 is an error; byte destinations swap the low 8 bits only
+          if (op == 0) fail("ZPAQL execution error");
+          if (ddd >= 4 && ddd <= 5) { U32 t = load(ddd); store(ddd, a); a = (a & ~255u) | t; }
+          else { U32 t = load(ddd); store(ddd, a); a = t; }
+          break;
+        case 1: store(ddd, load(ddd) + 1); break;
+        case 2: store(ddd, load(ddd) - 1); break;
+        case 3: store(ddd, ~load(ddd)); break;
+        case 4: store(ddd, 0); break;
+        case 7:
+          if (ddd < 4) store(ddd, r[header[pc++]]);                 // ddd=r n
+          else if (ddd == 4) { if (f) pc += ((header[pc] + 128) & 255) - 127; else ++pc; }   // JT
+          else if (ddd == 5) { if (!f) pc += ((header[pc] + 128) & 255) - 127; else ++pc; }  // JF
+          else r[header[pc++]] = a;                                  // R=A
+          break;
+        default: fail("ZPAQL execution error");
+      }
+      return 1;
+    }
+    if (op < 128) {  // 01dddsss assignment
+      int ddd = (op >> 3) & 7, s = op & 7;
+      if (ddd == 7) fail("ZPAQL execution error");
+      store(ddd, src(s));
+      return 1;
+    }
+    if (op == 255) {  // LJ
+      if ((pc = hbegin + header[pc] + 256 * header[pc + 1]) >= hend) fail("ZPAQL execution error");
+      return 1;
+    }
+    int x = (op >> 3) & 15;
+    if (x > 13) fail("ZPAQL execution error");
+    U32 v = src(op & 7);
+    switch (x) {
+      case 0: a += v; break;
+      case 1: a -= v; break;
+      case 2: a *= v; break;
+      case 3: a = v ? a / v : 0; break;
+      case 4: a = v ? a % v : 0; break;
+      case 5: a &= v; break;
+      case 6: a &= ~v; break;
+      case 7: a |= v; break;
+      case 8: a ^= v; break;
+      case 9: a <<= (v & 31); break;
+      case 10: a >>= (v & 31); break;
+      case 11: f = (a == v); break;
+      case 12: f = (a < v); break;
+      case 13: f = (a > v); break;
+    }
+    return 1;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Predictor.  Predictor.cs:39-172 (init), :245-350 (predict0), :353-475 (update0),
+// :486-493 + :1031-1036 (train, restored), :550-567 (find).
+// ---------------------------------------------------------------------------------------
+struct Component {  // Component.cs:20-25
+  size_t limit, cxt, a, b, c;
+  std::vector<U32> cm; Bytes ht; std::vector<U16> a16;
+  Component() : limit(0), cxt(0), a(0), b(0), c(0) {}
+};
+
+struct Predictor {
+  ZPAQL& z;
+  int c8, hmap4;
+  int p[256]; U32 h[256];
+  Component comp[256];
+  explicit Predictor(ZPAQL& z_) : z(z_), c8(1), hmap4(1) {}
+  bool isModeled() const { return z.header[6] != 0; }
+
+  void init() {
+    z.inith();
+    for (int i = 0; i < 256; ++i) { h[i] = 0; p[i] = 0; comp[i] = Component(); }
+    c8 = 1; hmap4 = 1;
+    int n = z.header[6];
+    const U8* cp = &z.header[7];
+    for (int i = 0; i < n; ++i) {
+      Component& cr = comp[i];
+      switch (cp[0]) {
+        case CONS: p[i] = (cp[1] - 128) * 4; break;
+        case CM:
+          if (cp[1] > 32) fail("max size for CM is 32");
+          cr.cm.assign((size_t)1 << cp[1], 0x80000000u);
+          cr.limit = cp[2] * 4;
+          break;
+        case ICM:
+          if (cp[1] > 26) fail("max size for ICM is 26");
+          cr.limit = 1023;
+          cr.cm.resize(256);
+          cr.ht.assign((size_t)64 << cp[1], 0);
+          for (int j = 0; j < 256; ++j) cr.cm[j] = st_cminit(j);
+          break;
+        case MATCH:
+          if (cp[1] > 32 || cp[2] > 32) fail("max size for MATCH is 32 32");
+          cr.cm.assign((size_t)1 << cp[1], 0);
+          cr.ht.assign((size_t)1 << cp[2], 0);
+          cr.ht[0] = 1;
+          break;
+        case AVG:
+          if (cp[1] >= i) fail("AVG j >= i");
+          if (cp[2] >= i) fail("AVG k >= i");
+          break;
+        case MIX2:
+          if (cp[1] > 32) fail("max size for MIX2 is 32");
+          if (cp[3] >= i) fail("MIX2 k >= i");
+          if (cp[2] >= i) fail("MIX2 j >= i");
+          cr.c = (size_t)1 << cp[1];
+          cr.a16.assign((size_t)1 << cp[1], 32768);
+          break;
+        case MIX: {
+          if (cp[1] > 32) fail("max size for MIX is 32");
+          if (cp[2] >= i) fail("MIX j >= i");
+          if (cp[3] < 1 || cp[3] > i - cp[2]) fail("MIX m not in 1..i-j");
+          int m = cp[3];
+          cr.c = (size_t)1 << cp[1];
+          cr.cm.assign((size_t)m << cp[1], 65536 / m);
+          break;
+        }
+        case ISSE:
+          if (cp[1] > 32) fail("max size for ISSE is 32");
+          if (cp[2] >= i) fail("ISSE j >= i");
+          cr.ht.assign((size_t)64 << cp[1], 0);
+          cr.cm.resize(512);
+          for (int j = 0; j < 256; ++j) {
+            cr.cm[j * 2] = 1 << 15;
+            cr.cm[j * 2 + 1] = (U32)clamp512k(stretch(st_cminit(j) >> 8) * 1024);
+          }
+          break;
+        case SSE:
+          if (cp[1] > 32) fail("max size for SSE is 32");
+          if (cp[2] >= i) fail("SSE j >= i");
+          if (cp[3] > cp[4] * 4) fail("SSE start > limit*4");
+          cr.cm.resize((size_t)32 << cp[1]);
+          cr.limit = cp[4] * 4;
+          for (size_t j = 0; j < cr.cm.size(); ++j) cr.cm[j] = (U32)squash((int)(j & 31) * 64 - 992) << 17 | cp[3];
+          break;
+        default: fail("unknown component type");
+      }
+      cp += compsize(cp[0]);
+    }
+  }
+
+  // Predictor.cs:550-567
+  static size_t find(Bytes& ht, int sizebits, U32 cxt) {
+    int chk = cxt >> sizebits & 255;
+    size_t h0 = ((size_t)cxt * 16) & (ht.size() - 16);
+    if (ht[h0] == chk) return h0;
+    size_t h1 = h0 ^ 16;
+    if (ht[h1] == chk) return h1;
+    size_t h2 = h0 ^ 32;
+    if (ht[h2] == chk) return h2;
+    if (ht[h0 + 1] <= ht[h1 + 1] && ht[h0 + 1] <= ht[h2 + 1]) { memset(&ht[h0], 0, 16); ht[h0] = (U8)chk; return h0; }
+    if (ht[h1 + 1] < ht[h2 + 1]) { memset(&ht[h1], 0, 16); ht[h1] = (U8)chk; return h1; }
+    memset(&ht[h2], 0, 16); ht[h2] = (U8)chk; return h2;
+  }
+
+  // Predictor.cs:245-350
+  int predict() {
+    int n = z.header[6];
+    const U8* cp = &z.header[7];
+    const Tables& t = T();
+    for (int i = 0; i < n; ++i) {
+      Component& cr = comp[i];
+      switch (cp[0]) {
+        case CONS: break;
+        case CM:
+          cr.cxt = h[i] ^ hmap4;
+          p[i] = t.stretch[cr.cm[cr.cxt & (cr.cm.size() - 1)] >> 17];
+          break;
+        case ICM:
+          if (c8 == 1 || (c8 & 0xf0) == 16) cr.c = find(cr.ht, cp[1] + 2, h[i] + 16 * c8);
+          cr.cxt = cr.ht[cr.c + (hmap4 & 15)];
+          p[i] = t.stretch[cr.cm[cr.cxt & 255] >> 8];
+          break;
+        case MATCH:
+          if (cr.a == 0) p[i] = 0;
+          else {
+            cr.c = (cr.ht[(cr.limit - cr.b) & (cr.ht.size() - 1)] >> (7 - cr.cxt)) & 1;
+            p[i] = t.stretch[t.dt2k[cr.a] * ((int)cr.c * -2 + 1) & 32767];
+          }
+          break;
+        case AVG:
+          p[i] = (p[cp[1]] * cp[3] + p[cp[2]] * (256 - cp[3])) >> 8;
+          break;
+        case MIX2: {
+          cr.cxt = ((h[i] + (c8 & cp[5])) & (cr.c - 1));
+          int w = cr.a16[cr.cxt];
+          p[i] = (w * p[cp[2]] + (65536 - w) * p[cp[3]]) >> 16;
+          break;
+        }
+        case MIX: {
+          int m = cp[3];
+          cr.cxt = h[i] + (c8 & cp[5]);
+          cr.cxt = (cr.cxt & (cr.c - 1)) * m;
+          int* wt = (int*)&cr.cm[cr.cxt];
+          p[i] = 0;
+          for (int j = 0; j < m; ++j) p[i] += (wt[j] >> 8) * p[cp[2] + j];
+          p[i] = clamp2k(p[i] >> 8);
+          break;
+        }
+        case ISSE: {
+          if (c8 == 1 || (c8 & 0xf0) == 16) cr.c = find(cr.ht, cp[1] + 2, h[i] + 16 * c8);
+          cr.cxt = cr.ht[cr.c + (hmap4 & 15)];
+          int* wt = (int*)&cr.cm[cr.cxt * 2];
+          p[i] = clamp2k((wt[0] * p[cp[2]] + wt[1] * 64) >> 16);
+          break;
+        }
+        case SSE: {
+          cr.cxt = (U32)((h[i] + c8) * 32);
+          int pq = p[cp[2]] + 992;
+          if (pq < 0) pq = 0;
+          if (pq > 1983) pq = 1983;
+          int wt = pq & 63;
+          pq >>= 6;
+          cr.cxt += pq;
+          size_t mask = cr.cm.size() - 1;
+          p[i] = t.stretch[((cr.cm[cr.cxt & mask] >> 10) * (64 - wt) + (cr.cm[(cr.cxt + 1) & mask] >> 10) * wt) >> 13];
+          cr.cxt += wt >> 5;
+          break;
+        }
+        default: fail("component predict not implemented");
+      }
+      cp += compsize(cp[0]);
+    }
+    return squash(p[n - 1]);
+  }
+
+  // restored: C++ original kept at Predictor.cs:1031-1036
+  void train(Component& cr, int y) {
+    U32& pn = cr.cm[cr.cxt & (cr.cm.size() - 1)];
+    U32 count = pn & 0x3ff;
+    int error = y * 32767 - (int)(pn >> 17);
+    pn += ((U32)error * (U32)T().dt[count] & 0xFFFFFC00u) + (count < cr.limit);
+  }
+
+  // Predictor.cs:353-475
+  void update(int y) {
+    const U8* cp = &z.header[7];
+    int n = z.header[6];
+    for (int i = 0; i < n; ++i) {
+      Component& cr = comp[i];
+      switch (cp[0]) {
+        case CONS: break;
+        case CM: train(cr, y); break;
+        case ICM: {
+          U8& bh = cr.ht[cr.c + (hmap4 & 15)];
+          bh = (U8)st_next(bh, y);
+          U32& pn = cr.cm[cr.cxt & 255];
+          pn += (U32)((int)(y * 32767 - (pn >> 8)) >> 2);
+          break;
+        }
+        case MATCH: {
+          size_t hm = cr.ht.size() - 1;
+          if ((int)cr.c != y) cr.a = 0;
+          cr.ht[cr.limit & hm] = (U8)(cr.ht[cr.limit & hm] * 2 + y);
+          if (++cr.cxt == 8) {
+            cr.cxt = 0;
+            ++cr.limit;
+            cr.limit &= ((size_t)1 << cp[2]) - 1;
+            if (cr.a == 0) {
+              cr.b = cr.limit - cr.cm[h[i] & (cr.cm.size() - 1)];
+              if (cr.b & hm)
+                while (cr.a < 255 && cr.ht[(cr.limit - cr.a - 1) & hm] == cr.ht[(cr.limit - cr.a - cr.b - 1) & hm]) ++cr.a;
+            } else cr.a += cr.a < 255;
+            cr.cm[h[i] & (cr.cm.size() - 1)] = (U32)cr.limit;
+          }
+          break;
+        }
+        case AVG: break;
+        case MIX2: {
+          int err = (y * 32767 - squash(p[i])) * cp[4] >> 5;
+          int w = cr.a16[cr.cxt];
+          w += (err * (p[cp[2]] - p[cp[3]]) + (1 << 12)) >> 13;
+          if (w < 0) w = 0;
+          if (w > 65535) w = 65535;
+          cr.a16[cr.cxt] = (U16)w;
+          break;
+        }
+        case MIX: {
+          int m = cp[3];
+          int err = (y * 32767 - squash(p[i])) * cp[4] >> 4;
+          int* wt = (int*)&cr.cm[cr.cxt];
+          for (int j = 0; j < m; ++j) wt[j] = clamp512k(wt[j] + ((err * p[cp[2] + j] + (1 << 12)) >> 13));
+          break;
+        }
+        case ISSE: {
+          int err = y * 32767 - squash(p[i]);
+          int* wt = (int*)&cr.cm[cr.cxt * 2];
+          wt[0] = clamp512k(wt[0] + ((err * p[cp[2]] + (1 << 12)) >> 13));
+          wt[1] = clamp512k(wt[1] + ((err + 16) >> 5));
+          cr.ht[cr.c + (hmap4 & 15)] = (U8)st_next((int)cr.cxt, y);
+          break;
+        }
+        case SSE: train(cr, y); break;
+      }
+      cp += compsize(cp[0]);
+    }
+    c8 += c8 + y;
+    if (c8 >= 256) {
+      z.run(c8 - 256);
+      hmap4 = 1; c8 = 1;
+      for (int i = 0; i < n; ++i) h[i] = z.H(i);
+    } else if (c8 >= 16 && c8 < 32) hmap4 = (hmap4 & 0xf) << 5 | y << 4 | 1;
+    else hmap4 = (hmap4 & 0x1f0) | (((hmap4 & 0xf) * 2 + y) & 0xf);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Arithmetic coder.  Encoder.cs:26-103, Decoder.cs:32-158.
+// ---------------------------------------------------------------------------------------
+struct Encoder {
+  Bytes* out; U32 low, high; Predictor pr; Bytes buf;
+  explicit Encoder(ZPAQL& z) : out(nullptr), low(1), high(0xFFFFFFFFu), pr(z) {}
+  void init() {
+    low = 1; high = 0xFFFFFFFFu;
+    pr.init();
+    if (!pr.isModeled()) { low = 0; buf.assign(1 << 16, 0); }
+  }
+  void encode(int y, int p) {
+    U32 mid = low + (U32)(((U64)(high - low) * (U32)p) >> 16);
+    if (y) high = mid; else low = mid + 1;
+    while ((high ^ low) < 0x1000000u) {
+      out->push_back((U8)(high >> 24));
+      high = high << 8 | 255;
+      low = low << 8;
+      low += (low == 0);
+    }
+  }
+  void compress(int c) {
+    if (pr.isModeled()) {
+      if (c == -1) encode(1, 0);
+      else {
+        encode(0, 0);
+        for (int i = 7; i >= 0; --i) {
+          int p = pr.predict() * 2 + 1;
+          int y = c >> i & 1;
+          encode(y, p);
+          pr.update(y);
+        }
+      }
+    } else {  // stored mode, Encoder.cs:58-72
+      if (low && (c < 0 || low == buf.size())) {
+        out->push_back((low >> 24) & 255); out->push_back((low >> 16) & 255);
+        out->push_back((low >> 8) & 255); out->push_back(low & 255);
+        out->insert(out->end(), buf.begin(), buf.begin() + low);
+        low = 0;
+      }
+      if (c >= 0) buf[low++] = (U8)c;
+    }
+  }
+};
+
+struct Decoder {
+  ByteSource* in; U32 low, high, curr; Predictor pr;
+  explicit Decoder(ZPAQL& z) : in(nullptr), low(1), high(0xFFFFFFFFu), curr(0), pr(z) {}
+  int get() { return in->get(); }
+  void init() {
+    pr.init();
+    if (pr.isModeled()) { low = 1; high = 0xFFFFFFFFu; curr = 0; }
+    else low = high = curr = 0;
+  }
+  int decode(int p) {
+    if (curr < low || curr > high) fail("archive corrupted");
+    U32 mid = low + (U32)(((U64)(high - low) * (U32)p) >> 16);
+    int y;
+    if (curr <= mid) { y = 1; high = mid; } else { y = 0; low = mid + 1; }
+    while ((high ^ low) < 0x1000000u) {
+      high = high << 8 | 255;
+      low = low << 8;
+      low += (low == 0);
+      int c = get();
+      if (c < 0) fail("unexpected end of file");
+      curr = curr << 8 | (U32)c;
+    }
+    return y;
+  }
+  int decompress() {
+    if (pr.isModeled()) {
+      if (curr == 0) for (int i = 0; i < 4; ++i) curr = curr << 8 | (U32)(get() & 255);
+      if (decode(0)) {
+        if (curr != 0) fail("decoding end of stream");
+        return -1;
+      }
+      int c = 1;
+      while (c < 256) {
+        int p = pr.predict() * 2 + 1;
+        c += c + decode(p);
+        pr.update(c & 1);
+      }
+      return c - 256;
+    }
+    if (curr == 0) {
+      for (int i = 0; i < 4; ++i) curr = curr << 8 | (U32)(get() & 255);
+      if (curr == 0) return -1;
+    }
+    --curr;
+    return get();
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// PostProcessor.  PostProcessor.cs:27-86.
+// ---------------------------------------------------------------------------------------
+struct PostProcessor {
+  int state, hsize, ph, pm; ZPAQL z;
+  PostProcessor() : state(0), hsize(0), ph(0), pm(0) {}
+  void init(int h, int m) { state = hsize = 0; ph = h; pm = m; Bytes* o = z.output; SHA1* s = z.sha1; z.clear(); z.output = o; z.sha1 = s; }
+  int write(int c) {
+    switch (state) {
+      case 0:
+        if (c < 0) fail("Unexpected EOS");
+        state = c + 1;
+        if (state > 2) fail("unknown post processing type");
+        break;
+      case 1: if (c >= 0) z.outc(c); break;
+      case 2:
+        if (c < 0) fail("Unexpected EOS");
+        hsize = c; state = 3; break;
+      case 3:
+        if (c < 0) fail("Unexpected EOS");
+        hsize += c * 256;
+        if (hsize < 1) fail("Empty PCOMP");
+        z.header.assign(hsize + 300, 0);
+        z.cend = 8;
+        z.hbegin = z.hend = z.cend + 128;
+        z.header[4] = (U8)ph; z.header[5] = (U8)pm;
+        state = 4; break;
+      case 4:
+        if (c < 0) fail("Unexpected EOS");
+        z.header[z.hend++] = (U8)c;
+        if (z.hend - z.hbegin == hsize) {
+          hsize = z.cend - 2 + z.hend - z.hbegin;
+          z.header[0] = hsize & 255; z.header[1] = hsize >> 8;
+          z.initp();
+          state = 5;
+        }
+        break;
+      case 5:
+        z.run((U32)c);
+        break;
+    }
+    return state;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Suffix array (any correct construction yields the unique result divsufsort.cs:1940 would).
+// Prefix doubling with std::sort; test-sized inputs only.  oracle/_ref/ optionally holds the
+// reference's own divsufsort built from divsufsort.cs for cross-checking (oracle/build_ref.sh).
+// ---------------------------------------------------------------------------------------
+static void suffix_array(const U8* s, int n, std::vector<int>& sa) {
+  sa.resize(n);
+  if (n == 0) return;
+  std::vector<int> rank(n), tmp(n);
+  for (int i = 0; i < n; ++i) { sa[i] = i; rank[i] = s[i]; }
+  for (int k = 1;; k <<= 1) {
+    auto key2 = [&](int i) { return i + k < n ? rank[i + k] : -1; };
+    auto cmp = [&](int x, int y) { return rank[x] != rank[y] ? rank[x] < rank[y] : key2(x) < key2(y); };
+    // sort only inside groups of equal rank (sa is already grouped by rank after round one)
+    if (k == 1) std::sort(sa.begin(), sa.end(), cmp);
+    else {
+      int i = 0;
+      while (i < n) {
+        int j = i + 1;
+        while (j < n && rank[sa[j]] == rank[sa[i]]) ++j;
+        if (j - i > 1) std::sort(sa.begin() + i, sa.begin() + j, [&](int x, int y) { return key2(x) < key2(y); });
+        i = j;
+      }
+    }
+    tmp[sa[0]] = 0;
+    for (int i = 1; i < n; ++i) tmp[sa[i]] = tmp[sa[i - 1]] + (cmp(sa[i - 1], sa[i]) ? 1 : 0);
+    // ranks must stay "first index of group" style so that groups remain contiguous: they do,
+    // since tmp is dense and monotone along sa.
+    rank = tmp;
+    if (rank[sa[n - 1]] == n - 1) break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// E8E9.  LibZPAQ.cs:372-384.
+// ---------------------------------------------------------------------------------------
+static void e8e9(U8* buf, int n) {
+  for (int i = n - 5; i >= 0; --i) {
+    if (((buf[i] & 254) == 0xe8) && ((buf[i + 4] + 1) & 254) == 0) {
+      unsigned a = (buf[i + 1] | buf[i + 2] << 8 | buf[i + 3] << 16) + i;
+      buf[i + 1] = (U8)a; buf[i + 2] = (U8)(a >> 8); buf[i + 3] = (U8)(a >> 16);
+    }
+  }
+}
+
+static int lg(U32 x) { int r = 0; while (x) { ++r; x >>= 1; } return r; }  // LZBuffer.cs:118-127
+
+// ---------------------------------------------------------------------------------------
+// LZ77 / BWT pre-processor.  LZBuffer.cs:151-222 (ctor), :225-384 (fill), :387-486 (codes).
+// Restated as a whole-block transform: the reference pauses whenever its 16 KB staging buffer
+// is half full, which never happens with literals pending, so the parse does not depend on it.
+// Bytes past the end of the block (read by the order-2 hash probe at LZBuffer.cs:291 without a
+// bound check) are taken as 0 here: `in` is a zero padded copy.
+// ---------------------------------------------------------------------------------------
+struct LZ {
+  std::vector<U8> inbuf; const U8* in; unsigned n;
+  int level; unsigned minMatch, minMatch2, maxMatch, maxLiteral, lookahead, bucket, shift1, shift2, rb;
+  int checkbits, minMatchBoth;
+  std::vector<U32> ht; unsigned htsize;
+  std::vector<int> sa; std::vector<U32> isa; bool useSA;
+  Bytes& out; U32 bits; unsigned nbits;
+
+  LZ(const U8* src, unsigned n_, const int args[9], Bytes& out_) : n(n_), out(out_), bits(0), nbits(0) {
+    inbuf.assign((size_t)n + 64, 0);
+    if (n) memcpy(inbuf.data(), src, n);
+    in = inbuf.data();
+    level = args[1] & 3;
+    minMatch = args[2]; minMatch2 = args[3];
+    maxMatch = (1 << 14) * 3; maxLiteral = (1 << 14) / 4;
+    lookahead = args[6];
+    bucket = (1u << args[4]) - 1;
+    shift1 = minMatch > 0 ? (args[5] - 1) / minMatch + 1 : 1;
+    shift2 = minMatch2 > 0 ? (args[5] - 1) / minMatch2 + 1 : 0;
+    minMatchBoth = (int)std::max(minMatch, minMatch2 + lookahead) + 4;
+    rb = args[0] > 4 ? args[0] - 4 : 0;
+    useSA = (args[5] - args[0] >= 21);
+    checkbits = !useSA ? 12 - args[0] : 17 + args[0];
+    if ((minMatch < 4 && level == 1) || (minMatch < 1 && level == 2)) fail("match length $3 too small");
+    if (args[1] > 4) e8e9(inbuf.data(), (int)n);  // LZBuffer.cs:198
+    if (useSA || level == 3) suffix_array(in, (int)n, sa);
+    if (level < 3) {
+      if (useSA) isa.assign((size_t)1 << 17 << args[0], 0);
+      else { htsize = 1u << args[5]; ht.assign(htsize, 0); }
+    }
+  }
+  void putb(U32 x, int k) {
+    x &= (1u << k) - 1;
+    bits |= x << nbits;
+    nbits += k;
+    while (nbits > 7) { out.push_back((U8)bits); bits >>= 8; nbits -= 8; }
+  }
+  void flush() { if (nbits > 0) out.push_back((U8)bits); bits = nbits = 0; }
+  void put(int c) { out.push_back((U8)c); }
+
+  void write_literal(unsigned i, unsigned& lit) {  // LZBuffer.cs:387-419
+    if (level == 1) {
+      if (lit < 1) return;
+      int ll = lg(lit);
+      putb(0, 2);
+      --ll;
+      while (--ll >= 0) { putb(1, 1); putb((lit >> ll) & 1, 1); }
+      putb(0, 1);
+      while (lit) putb(in[i - lit--], 8);
+    } else {
+      while (lit > 0) {
+        unsigned lit1 = lit > 64 ? 64 : lit;
+        put(lit1 - 1);
+        for (unsigned j = i - lit; j < i - lit + lit1; ++j) put(in[j]);
+        lit -= lit1;
+      }
+    }
+  }
+  void write_match(unsigned len, unsigned off) {  // LZBuffer.cs:422-486
+    if (level == 1) {
+      int ll = lg(len) - 1;
+      off += (1 << rb) - 1;
+      int lo = lg(off) - 1 - rb;
+      putb((lo + 8) >> 3, 2);
+      putb(lo & 7, 3);
+      while (--ll >= 2) { putb(1, 1); putb((len >> ll) & 1, 1); }
+      putb(0, 1);
+      putb(len & 3, 2);
+      putb(off, rb);
+      putb(off >> rb, lo);
+    } else {
+      --off;
+      while (len > 0) {
+        const unsigned len1 = len > minMatch * 2 + 63 ? minMatch + 63 : len > minMatch + 63 ? len - minMatch : len;
+        if (off < (1 << 16)) { put(64 + len1 - minMatch); put(off >> 8); put(off); }
+        else if (off < (1 << 24)) { put(128 + len1 - minMatch); put(off >> 16); put(off >> 8); put(off); }
+        else { put(192 + len1 - minMatch); put(off >> 24); put(off >> 16); put(off >> 8); put(off); }
+        len -= len1;
+      }
+    }
+  }
+
+  void run() {
+    if (level == 3) {  // BWT, LZBuffer.cs:229-241
+      U32 idx = 0;
+      for (unsigned i = 0; i < n + 5; ++i) {
+        if (i == 0) put(n > 0 ? in[n - 1] : 255);
+        else if (i > n) { put(idx & 255); idx >>= 8; }
+        else if (sa[i - 1] == 0) { idx = i; put(255); }
+        else put(in[sa[i - 1] - 1]);
+      }
+      return;
+    }
+    unsigned i = 0, lit = 0, h1 = 0, h2 = 0;
+    const unsigned mask = (1u << checkbits) - 1;
+    while (i < n) {
+      unsigned blen = minMatch - 1, bp = 0, blit = 0;
+      int bscore = 0;
+      if (useSA) {  // LZBuffer.cs:255-283
+        if ((unsigned)sa[isa[i & mask]] != i)
+          for (unsigned j = 0; j < n; ++j)
+            if (((unsigned)sa[j] & ~mask) == (i & ~mask)) isa[sa[j] & mask] = j;
+        for (unsigned h = 0; h <= lookahead; ++h) {
+          unsigned q = isa[(h + i) & mask];
+          if ((unsigned)sa[q] != h + i) continue;
+          for (int j = -1; j <= 1; j += 2) {
+            for (unsigned k = 1; k <= bucket; ++k) {
+              unsigned p;
+              if (q + j * k < n && (p = sa[q + j * k] - h) < i) {
+                unsigned l, l1;
+                for (l = h; i + l < n && l < maxMatch && in[p + l] == in[i + l]; ++l) {}
+                for (l1 = h; l1 > 0 && in[p + l1 - 1] == in[i + l1 - 1]; --l1) {}
+                int score = int(l - l1) * 8 - lg(i - p) - 4 * (lit == 0 && l1 > 0) - 11;
+                for (unsigned a = 0; a < h; ++a) score = score * 5 / 8;
+                if (score > bscore) { blen = l; bp = p; blit = l1; bscore = score; }
+                if (l < blen || l < minMatch || l > 255) break;
+              }
+            }
+          }
+          if (bscore <= 0 || blen < minMatch) break;
+        }
+      } else if (level == 1 || minMatch <= 64) {  // LZBuffer.cs:288-327
+        if (minMatch2 > 0) {
+          for (unsigned k = 0; k <= bucket; ++k) {
+            unsigned p = ht[h2 ^ k];
+            if (p && (p & mask) == (in[i + 3] & mask)) {
+              p >>= checkbits;
+              if (p < i && i + blen <= n && in[p + blen - 1] == in[i + blen - 1]) {
+                unsigned l;
+                for (l = lookahead; i + l < n && l < maxMatch && in[p + l] == in[i + l]; ++l) {}
+                if (l >= minMatch2 + lookahead) {
+                  int l1;
+                  for (l1 = lookahead; l1 > 0 && in[p + l1 - 1] == in[i + l1 - 1]; --l1) {}
+                  int score = int(l - l1) * 8 - lg(i - p) - 8 * (lit == 0 && l1 > 0) - 11;
+                  if (score > bscore) { blen = l; bp = p; blit = l1; bscore = score; }
+                }
+              }
+            }
+            if (blen >= 128) break;
+          }
+        }
+        if (!minMatch2 || blen < minMatch2) {
+          for (unsigned k = 0; k <= bucket; ++k) {
+            unsigned p = ht[h1 ^ k];
+            if (p && i + 3 < n && (p & mask) == (in[i + 3] & mask)) {
+              p >>= checkbits;
+              if (p < i && i + blen <= n && in[p + blen - 1] == in[i + blen - 1]) {
+                unsigned l;
+                for (l = 0; i + l < n && l < maxMatch && in[p + l] == in[i + l]; ++l) {}
+                int score = l * 8 - lg(i - p) - 2 * (lit > 0) - 11;
+                if (score > bscore) { blen = l; bp = p; blit = 0; bscore = score; }
+              }
+            }
+            if (blen >= 128) break;
+          }
+        }
+      }
+      const unsigned off = i - bp;  // LZBuffer.cs:331-346
+      if (off > 0 && bscore > 0 && blen - blit >= minMatch + (level == 2) * ((off >= (1 << 16)) + (off >= (1 << 24)))) {
+        lit += blit;
+        write_literal(i + blit, lit);
+        write_match(blen - blit, off);
+      } else { blen = 1; ++lit; }
+      if (useSA) i += blen;
+      else {  // LZBuffer.cs:349-368
+        while (blen--) {
+          if (i + minMatchBoth < n) {
+            unsigned ih = ((i * 1234547) >> 19) & bucket;
+            const unsigned p = (i << checkbits) | (in[i + 3] & mask);
+            if (minMatch2) {
+              ht[h2 ^ ih] = p;
+              h2 = (((h2 * 9) << shift2) + (in[i + minMatch2 + lookahead] + 1) * 23456789u) & (htsize - 1);
+            }
+            ht[h1 ^ ih] = p;
+            h1 = (((h1 * 5) << shift1) + (in[i + minMatch] + 1) * 123456791u) & (htsize - 1);
+          }
+          ++i;
+        }
+      }
+      if (lit >= maxLiteral) write_literal(i, lit);
+    }
+    write_literal(n, lit);
+    flush();
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Block framing.  Compressor.cs:27-299 as driven by compressBlock, LibZPAQ.cs:286-324.
+//   hdr    : block header on the wire (hsize.. COMP 0 HCOMP 0), i.e. ZPAQL.write(out,false)
+//   pcomp  : PCOMP program bytes (without the 2 length bytes) or empty
+//   args   : the 9 method arguments ($1..$9) after makeConfig
+// ---------------------------------------------------------------------------------------
+static const U8 kTag[13] = {0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3};
+
+static void preprocess(const U8* in, unsigned n, const int args[9], Bytes& out) {  // LibZPAQ.cs:301-312
+  if (args[1] >= 1 && args[1] <= 7 && args[1] != 4) {
+    LZ lz(in, n, args, out);
+    lz.run();
+  } else {
+    out.assign(in, in + n);
+    if (args[1] >= 4 && args[1] <= 7) e8e9(out.data(), (int)n);
+  }
+}
+
+static void compress_block(const U8* hdr, size_t hlen, const U8* pcomp, size_t plen, const int args[9],
+                           const U8* in, unsigned n, const char* filename, const char* comment,
+                           int dosha1, int with_tag, Bytes& out) {
+  ZPAQL z;
+  ByteSource hs(hdr, hlen);
+  z.read(hs);
+  U8 sha[20];
+  if (dosha1) { SHA1 s; s.write(in, n); s.result(sha); }
+  if (with_tag) out.insert(out.end(), kTag, kTag + 13);   // Compressor.cs:27-43
+  out.push_back('z'); out.push_back('P'); out.push_back('Q');  // Compressor.cs:109-113
+  out.push_back(1 + (z.header[6] == 0));
+  out.push_back(1);
+  z.write(out, false);
+  out.push_back(1);                                         // Compressor.cs:133-146
+  for (const char* s = filename; s && *s; ++s) out.push_back((U8)*s);
+  out.push_back(0);
+  for (const char* s = comment; s && *s; ++s) out.push_back((U8)*s);
+  out.push_back(0);
+  out.push_back(0);
+  Bytes data;
+  preprocess(in, n, args, data);
+  Encoder enc(z);
+  enc.out = &out;
+  enc.init();                                               // Compressor.cs:156-190
+  if (plen > 0) {
+    enc.compress(1);
+    enc.compress((int)(plen & 255));
+    enc.compress((int)((plen >> 8) & 255));
+    for (size_t i = 0; i < plen; ++i) enc.compress(pcomp[i]);
+  } else enc.compress(0);
+  for (size_t i = 0; i < data.size(); ++i) enc.compress(data[i]);  // Compressor.cs:193-221
+  enc.compress(-1);                                         // Compressor.cs:224-248
+  out.push_back(0); out.push_back(0); out.push_back(0); out.push_back(0);
+  if (dosha1) { out.push_back(253); out.insert(out.end(), sha, sha + 20); }
+  else out.push_back(254);
+  out.push_back(255);                                       // Compressor.cs:294-299
+}
+
+// Decompresser.cs:29-194 driven by LibZPAQ.decompress, LibZPAQ.cs:65-79.  Decodes every block
+// and segment in `arc`; appends output to `out`; verifies stored SHA-1s; returns the number of
+// blocks; sha_status (if not null) receives per segment 0=no checksum 1=match 2=mismatch.
+static int decompress_all(const U8* arc, size_t n, Bytes& out, Bytes* sha_status) {
+  ByteSource in(arc, n);
+  int blocks = 0;
+  for (;;) {
+    U32 h1 = 0x3D49B113, h2 = 0x29EB7F93, h3 = 0x2614BE13, h4 = 0x3828EB13;  // Decompresser.cs:34
+    int c;
+    while ((c = in.get()) != -1) {
+      h1 = h1 * 12 + c; h2 = h2 * 20 + c; h3 = h3 * 28 + c; h4 = h4 * 44 + c;
+      if (h1 == 0xB16B88F1 && h2 == 0xFF5376F1 && h3 == 0x72AC5BF1 && h4 == 0x2F909AF1) break;
+    }
+    if (c == -1) break;
+    if ((c = in.get()) != 1 && c != 2) fail("unsupported ZPAQ level");
+    if (in.get() != 1) fail("unsupported ZPAQL type");
+    ZPAQL z;
+    z.read(in);
+    if (c == 1 && z.header.size() > 6 && z.header[6] == 0) fail("ZPAQ level 1 requires at least 1 component");
+    ++blocks;
+    Decoder dec(z);
+    dec.in = &in;
+    PostProcessor pp;
+    bool first = true;
+    for (;;) {  // segments, Decompresser.cs:67-93
+      c = in.get();
+      if (c == 255) break;
+      if (c != 1) fail("missing segment or end of block");
+      while ((c = in.get()) != 0) if (c == -1) fail("unexpected EOF");
+      while ((c = in.get()) != 0) if (c == -1) fail("unexpected EOF");  // comment :96-108
+      if (in.get() != 0) fail("missing reserved byte");
+      size_t seg_start = out.size();
+      SHA1 sha;
+      pp.z.output = &out;
+      pp.z.sha1 = &sha;
+      if (first) { dec.init(); pp.init(z.header[4], z.header[5]); first = false; }  // :128-134
+      while ((pp.state & 3) != 1) pp.write(dec.decompress());
+      for (;;) {
+        int ch = dec.decompress();
+        pp.write(ch);
+        if (ch == -1) break;
+      }
+      (void)seg_start;
+      c = in.get();                                           // readSegmentEnd :163-194
+      if (c == 254) { if (sha_status) sha_status->push_back(0); }
+      else if (c == 253) {
+        U8 want[20], got[20];
+        for (int i = 0; i < 20; ++i) want[i] = (U8)in.get();
+        sha.result(got);
+        if (sha_status) sha_status->push_back(memcmp(want, got, 20) == 0 ? 1 : 2);
+      } else fail("missing end of segment marker");
+    }
+  }
+  return blocks;
+}
+
+}  // namespace orc
+
+// =========================================================================================
+// C interface used by tests (ctypes) and by bench.py's CPU baseline.
+// All functions return >= 0 on success, -1 on error (message via orc_last_error()).
+// =========================================================================================
+static thread_local std::string g_err;
+#define ORC_TRY try {
+#define ORC_CATCH } catch (const std::exception& e) { g_err = e.what(); return -1; }
+
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+int orc_tables(uint16_t* squash4096, int16_t* stretch32768, int* dt1024, int* dt2k256, uint8_t* ns1024) {
+  ORC_TRY
+  const orc::Tables& t = orc::T();
+  if (squash4096) memcpy(squash4096, t.squash, sizeof(t.squash));
+  if (stretch32768) memcpy(stretch32768, t.stretch, sizeof(t.stretch));
+  if (dt1024) memcpy(dt1024, t.dt, sizeof(t.dt));
+  if (dt2k256) memcpy(dt2k256, t.dt2k, sizeof(t.dt2k));
+  if (ns1024) memcpy(ns1024, t.ns, sizeof(t.ns));
+  return 0;
+  ORC_CATCH
+}
+
+int orc_cminit(int state) { return orc::st_cminit(state); }
+
+void orc_sha1(const uint8_t* p, uint64_t n, uint8_t out[20]) { orc::SHA1 s; s.write(p, n); s.result(out); }
+
+void orc_e8e9(uint8_t* buf, int n) { orc::e8e9(buf, n); }
+
+int orc_suffix_array(const uint8_t* s, int n, int* sa) {
+  ORC_TRY
+  std::vector<int> v; orc::suffix_array(s, n, v);
+  if (n) memcpy(sa, v.data(), sizeof(int) * (size_t)n);
+  return 0;
+  ORC_CATCH
+}
+
+// Pre-processing only (LZ77 / BWT / E8E9 as selected by args[1]); returns the output length.
+int64_t orc_preprocess(const uint8_t* in, uint32_t n, const int* args9, uint8_t* out, uint64_t cap) {
+  ORC_TRY
+  orc::Bytes o; orc::preprocess(in, n, args9, o);
+  if (o.size() > cap) orc::fail("oracle: output buffer too small");
+  if (!o.empty()) memcpy(out, o.data(), o.size());
+  return (int64_t)o.size();
+  ORC_CATCH
+}
+
+double orc_block_memory(const uint8_t* hdr, uint64_t hlen) {
+  try { orc::ZPAQL z; orc::ByteSource s(hdr, hlen); z.read(s); return z.memory(); }
+  catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int64_t orc_compress_block(const uint8_t* hdr, uint64_t hlen, const uint8_t* pcomp, uint64_t plen,
+                           const int* args9, const uint8_t* in, uint32_t n, const char* filename,
+                           const char* comment, int dosha1, int with_tag, uint8_t* out, uint64_t cap) {
+  ORC_TRY
+  orc::Bytes o;
+  orc::compress_block(hdr, hlen, pcomp, plen, args9, in, n, filename, comment, dosha1, with_tag, o);
+  if (o.size() > cap) orc::fail("oracle: output buffer too small");
+  memcpy(out, o.data(), o.size());
+  return (int64_t)o.size();
+  ORC_CATCH
+}
+
+// Decompress a whole archive (any number of blocks/segments).  sha_status gets one byte per
+// segment (0 none, 1 ok, 2 mismatch), up to sha_cap entries; *nseg receives the segment count.
+int64_t orc_decompress(const uint8_t* arc, uint64_t n, uint8_t* out, uint64_t cap, uint8_t* sha_status,
+                       uint32_t sha_cap, uint32_t* nseg) {
+  ORC_TRY
+  orc::Bytes o, st;
+  orc::decompress_all(arc, n, o, &st);
+  if (o.size() > cap) orc::fail("oracle: output buffer too small");
+  if (!o.empty()) memcpy(out, o.data(), o.size());
+  if (nseg) *nseg = (uint32_t)st.size();
+  for (size_t i = 0; i < st.size() && i < sha_cap; ++i) sha_status[i] = st[i];
+  return (int64_t)o.size();
+  ORC_CATCH
+}
+
+// Run a ZPAQL program (HCOMP of `hdr` when pp==0; or a bare PCOMP program when pp==1 with
+// ph/pm taken from hdr[4..5]) over `input`, calling run(byte) per byte and, if eof_call,
+// run(0xFFFFFFFF) at the end.  Returns OUT bytes in `out` and the final H[0..hn) in hout.
+int64_t orc_zpaql_run(const uint8_t* hdr, uint64_t hlen, int pp, const uint8_t* input, uint64_t n, int eof_call,
+                      uint8_t* out, uint64_t cap, uint32_t* hout, uint32_t hn) {
+  ORC_TRY
+  orc::ZPAQL z; orc::ByteSource s(hdr, hlen); z.read(s);
+  orc::Bytes o; z.output = &o;
+  if (pp) z.initp(); else z.inith();
+  for (uint64_t i = 0; i < n; ++i) z.run(input[i]);
+  if (eof_call) z.run(0xFFFFFFFFu);
+  for (uint32_t i = 0; i < hn; ++i) hout[i] = z.H(i);
+  if (o.size() > cap) orc::fail("oracle: output buffer too small");
+  if (!o.empty()) memcpy(out, o.data(), o.size());
+  return (int64_t)o.size();
+  ORC_CATCH
+}
+
+// Predictor trace: feeds `input` bytes through the model in `hdr` and records the 16-bit
+// probability handed to the coder for every bit (8 per byte).  Used to localise mismatches.
+int64_t orc_predict_trace(const uint8_t* hdr, uint64_t hlen, const uint8_t* input, uint64_t n, uint16_t* probs) {
+  ORC_TRY
+  orc::ZPAQL z; orc::ByteSource s(hdr, hlen); z.read(s);
+  orc::Predictor pr(z); pr.init();
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < n; ++i)
+    for (int b = 7; b >= 0; --b) { probs[k++] = (uint16_t)(pr.predict() * 2 + 1); pr.update(input[i] >> b & 1); }
+  return (int64_t)k;
+  ORC_CATCH
+}
+
+}  // extern "C"
