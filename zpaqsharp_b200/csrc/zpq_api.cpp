@@ -1,0 +1,899 @@
+// zpq_api.cpp -- C ABI of libzpaqb200 and the host scheduler behind it.
+//
+// The scheduler turns a batch of independent archive blocks into device work:
+//   compress:   H2D -> [SHA-1] -> [E8E9] -> encode kernel (one warp per resident block, atomic
+//               block queue) -> frame assembly -> scan -> gather -> D2H
+//   decompress: host parses block/segment framing (a few hundred bytes per block), H2D ->
+//               decode kernel (+ ZPAQL post-processing on the device) -> [SHA-1] -> scan ->
+//               gather -> D2H
+// Blocks never communicate, so multi-GPU use is a plain partition of the block list; results are
+// concatenated in block order (no collective).
+//
+// There is no CPU fallback: every entry point that touches block data fails when CUDA fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "zpq_device.h"
+#include "zpq_host.h"
+
+using namespace zpq;
+
+namespace {
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      throw Failure(e__ == cudaErrorMemoryAllocation ? ZPQ_E_NOMEM : ZPQ_E_CUDA,                   \
+                    std::string(#expr) + ": " + cudaGetErrorString(e__));                          \
+  } while (0)
+
+std::string g_create_error;
+std::mutex g_create_mutex;
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  uint64_t cap = 0;
+  void reserve(uint64_t bytes) {
+    if (bytes <= cap) return;
+    release();
+    CU(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Reserve an I/O buffer; if the device is full because an earlier call's state arenas still hold
+// the memory, drop them and try again.
+void reserve_io(DevBuf& b, uint64_t bytes, DevBuf& arena) {
+  try { b.reserve(bytes); }
+  catch (const Failure& f) {
+    if (f.code != ZPQ_E_NOMEM || !arena.p) throw;
+    cudaGetLastError();
+    arena.release();
+    b.reserve(bytes);
+  }
+}
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  void init() { CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); }
+  void fini() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
+  void start(cudaStream_t s) { CU(cudaEventRecord(a, s)); }
+  void stop(cudaStream_t s) { CU(cudaEventRecord(b, s)); }
+  double ms() const { float t = 0; cudaEventElapsedTime(&t, a, b); return t; }
+};
+
+struct Device {
+  int id = 0;
+  cudaStream_t own = nullptr, stream = nullptr;
+  int sms = 0;
+  uint32_t smem_optin = 0;
+  Tables* d_tab = nullptr;
+  DevBuf arena, in, work, slots, out, meta, plan;
+  Timer t_all, t_h2d, t_kern, t_codec, t_d2h;
+  zpq_stats stats{};
+
+  void init(int dev) {
+    id = dev;
+    CU(cudaSetDevice(id));
+    CU(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    stream = own;
+    int v = 0;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, id)); sms = v;
+    CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, id)); smem_optin = (uint32_t)v;
+    CU(codec_set_smem_limit(smem_optin));
+    std::unique_ptr<Tables> t(new Tables);
+    build_tables(*t);
+    CU(cudaMalloc(&d_tab, sizeof(Tables)));
+    CU(cudaMemcpy(d_tab, t.get(), sizeof(Tables), cudaMemcpyHostToDevice));
+    t_all.init(); t_h2d.init(); t_kern.init(); t_codec.init(); t_d2h.init();
+  }
+  void fini() {
+    cudaSetDevice(id);
+    arena.release(); in.release(); work.release(); slots.release(); out.release(); meta.release(); plan.release();
+    if (d_tab) cudaFree(d_tab);
+    t_all.fini(); t_h2d.fini(); t_kern.fini(); t_codec.fini(); t_d2h.fini();
+    if (own) cudaStreamDestroy(own);
+  }
+};
+
+// A model as the codec needs it.
+struct Model {
+  Header hdr;
+  Bytes pcomp;     // program incl. END, may be empty
+  int args[9];
+};
+
+// Geometry of a codec launch for `want` blocks of this model.
+struct Launch {
+  std::unique_ptr<Plan> plan;
+  SmemLayout sm;
+  LaunchGeom geom;
+  uint32_t resident;
+};
+
+uint32_t common_smem(const Plan& pl, SmemLayout& L) {
+  uint32_t o = 0;
+  L.stretch = 0; L.squash = 65536; L.dt = 73728; L.dt2k = 77824; L.ns = 78336;
+  o = 79360;
+  L.comp = o; o += (uint32_t)align_up((uint64_t)std::max(pl.n, 1) * sizeof(CompDesc), 16);
+  L.order = o; o += (uint32_t)align_up(std::max(pl.n, 1), 16);
+  L.steps = o; o += (uint32_t)align_up((uint64_t)std::max(pl.nsteps, 1) * sizeof(Step), 16);
+  if (pl.hcomp_len + 8 <= 4096) { L.hcomp = o; o += (uint32_t)align_up(pl.hcomp_len + 8, 16); }
+  else L.hcomp = kNoSmem;
+  return (uint32_t)align_up(o, 128);
+}
+
+void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint64_t mem_for_arenas, uint32_t max_resident,
+                 Launch& L) {
+  L.plan.reset(new Plan);
+  build_plan(hdr, decode, 48 * 1024, *L.plan);
+  uint64_t fit = mem_for_arenas / std::max<uint64_t>(L.plan->arena_bytes, 1);
+  if (fit < 1) throw Failure(ZPQ_E_NOMEM, "model state does not fit in device memory");
+  uint64_t resident = std::min<uint64_t>({want, fit, (uint64_t)d.sms * 16});
+  if (max_resident) resident = std::min<uint64_t>(resident, max_resident);
+  if (resident < 1) resident = 1;
+  uint32_t W = (uint32_t)((resident + d.sms - 1) / d.sms);
+  W = std::max(1u, std::min(16u, W));
+  for (;;) {
+    uint32_t common = common_smem(*L.plan, L.sm);
+    uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
+    if ((uint64_t)W * L.plan->smem_warp_bytes <= avail) break;
+    uint32_t budget = avail / W;
+    uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64, 128);
+    if (budget >= minimal) {
+      build_plan(hdr, decode, budget & ~127u, *L.plan);
+      common = common_smem(*L.plan, L.sm);
+      avail = d.smem_optin > common ? d.smem_optin - common : 0;
+      if ((uint64_t)W * L.plan->smem_warp_bytes <= avail) break;
+    }
+    if (W == 1) throw Failure(ZPQ_E_UNSUPPORTED, "model needs more shared memory than one SM has");
+    --W;
+  }
+  resident = std::min<uint64_t>(resident, (uint64_t)W * d.sms);
+  L.sm.slices = common_smem(*L.plan, L.sm);
+  L.sm.slice_bytes = L.plan->smem_warp_bytes;
+  L.sm.total = L.sm.slices + W * L.sm.slice_bytes;
+  L.geom.warps_per_cta = W;
+  L.geom.grid = (uint32_t)((resident + W - 1) / W);
+  L.resident = (uint32_t)resident;
+}
+
+uint64_t free_device_memory() {
+  size_t fr = 0, tot = 0;
+  CU(cudaMemGetInfo(&fr, &tot));
+  return fr;
+}
+
+}  // namespace
+
+struct zpq_ctx {
+  std::vector<Device> devs;
+  std::string err;
+  uint32_t max_resident = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Compression of blocks [first, first+count) of one model on one device.
+// Input either on the host (h_in) or already on the device (d_in_ext).  Output frames are
+// gathered into d_out (device) and, for host calls, copied to h_out + h_out_base.
+// Returns total frame bytes; frame_off[0..count] (relative) is filled.
+// ------------------------------------------------------------------------------------------
+struct CompressTask {
+  const Model* model;
+  const uint8_t* h_in = nullptr;        // host input base (offsets are absolute into it)
+  const uint8_t* d_in_ext = nullptr;    // or device input base
+  const uint64_t* in_off = nullptr;     // host array, absolute offsets, nb+1 entries overall
+  uint32_t first = 0, count = 0;
+  std::vector<std::string> filenames, comments;  // per block of this task (may be empty strings)
+  bool dosha1 = true, with_tag = true;
+  uint8_t* d_out_ext = nullptr;         // device output (dev variant) or null
+  uint64_t d_out_cap = 0;
+  std::vector<uint64_t> frame_off;      // out: count+1
+};
+
+void build_prefix(const Model& m, const std::string& filename, const std::string& comment, bool with_tag, Bytes& out) {
+  if (with_tag) out.insert(out.end(), kLocatorTag, kLocatorTag + 13);          // Compressor.cs:27-43
+  out.push_back('z'); out.push_back('P'); out.push_back('Q');                  // Compressor.cs:109-113
+  out.push_back((uint8_t)(1 + (m.hdr.n == 0)));
+  out.push_back(1);
+  out.insert(out.end(), m.hdr.wire.begin(), m.hdr.wire.end());                 // ZPAQL.write, ZPAQL.cs:158-179
+  out.push_back(1);                                                            // Compressor.cs:133-146
+  out.insert(out.end(), filename.begin(), filename.end()); out.push_back(0);
+  out.insert(out.end(), comment.begin(), comment.end()); out.push_back(0);
+  out.push_back(0);
+}
+
+uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h_out, uint64_t h_out_cap) {
+  CU(cudaSetDevice(d.id));
+  cudaStream_t s = d.stream;
+  const Model& M = *T.model;
+  const uint32_t nb = T.count;
+  const uint64_t* off = T.in_off + T.first;
+  const uint64_t in_base = off[0], in_total = off[nb] - off[0];
+  d.stats = zpq_stats{};
+  d.t_all.start(s);
+
+  const int pre = M.args[1];
+  if (pre != 0 && pre != 4)
+    throw Failure(ZPQ_E_UNSUPPORTED, "LZ77/BWT pre-processing (method argument 2 = " + std::to_string(pre) +
+                                         ") is not available in this build");
+
+  // ---- host-side metadata: preamble, prefixes, jobs ----
+  Bytes preamble;
+  if (!M.pcomp.empty()) {                                                      // Compressor.cs:177-188
+    preamble.push_back(1);
+    preamble.push_back((uint8_t)(M.pcomp.size() & 255));
+    preamble.push_back((uint8_t)(M.pcomp.size() >> 8));
+    preamble.insert(preamble.end(), M.pcomp.begin(), M.pcomp.end());
+  } else preamble.push_back(0);
+
+  Bytes prefix;
+  std::vector<uint32_t> prefix_off(nb + 1);
+  std::vector<EncJob> jobs(nb);
+  std::vector<uint64_t> slot_off(nb + 1), rel_off(nb);
+  std::vector<uint32_t> lens(nb);
+  uint64_t slots_total = 0, max_frame = 0;
+  for (uint32_t i = 0; i < nb; ++i) {
+    const uint64_t n = off[i + 1] - off[i];
+    if (n > 0xFFFFFFFFull - 8192) throw Failure(ZPQ_E_ARG, "block larger than 4 GiB");
+    prefix_off[i] = (uint32_t)prefix.size();
+    const std::string& cm = T.comments.size() > i && !T.comments[i].empty() ? T.comments[i] : std::to_string(n);
+    build_prefix(M, T.filenames.size() > i ? T.filenames[i] : std::string(), cm, T.with_tag, prefix);
+    const uint32_t plen = (uint32_t)prefix.size() - prefix_off[i];
+    const uint64_t stream = n + preamble.size();
+    const uint64_t cap = M.hdr.n ? stream + stream / 4 + 4096 : stream + 4 * (stream / 65536 + 1) + 16;
+    slot_off[i] = slots_total;
+    jobs[i].in_off = off[i] - in_base;
+    jobs[i].in_len = (uint32_t)n;
+    jobs[i].pre_len = (uint32_t)preamble.size();
+    jobs[i].out_off = slots_total + plen;
+    jobs[i].out_cap = cap;
+    rel_off[i] = off[i] - in_base;
+    lens[i] = (uint32_t)n;
+    const uint64_t frame = plen + cap + 32;
+    max_frame = std::max(max_frame, frame);
+    slots_total = align_up(slots_total + frame, 16);
+  }
+  prefix_off[nb] = (uint32_t)prefix.size();
+  slot_off[nb] = slots_total;
+
+  // ---- device buffers ----
+  // meta layout: jobs | slot_off | rel_off | lens | prefix_off | prefix | preamble | results | digests | frame_len | frame_off | queue
+  uint64_t mo = 0;
+  auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
+  const uint64_t o_jobs = place(sizeof(EncJob) * nb), o_slot = place(8ull * (nb + 1)), o_rel = place(8ull * nb),
+                 o_len = place(4ull * nb), o_poff = place(4ull * (nb + 1)), o_prefix = place(prefix.size()),
+                 o_pre = place(preamble.size()), o_res = place(sizeof(BlockResult) * nb), o_dig = place(20ull * nb),
+                 o_flen = place(8ull * nb), o_foff = place(8ull * (nb + 1)), o_queue = place(256);
+  reserve_io(d.meta, mo, d.arena);
+  uint8_t* meta = d.meta.as<uint8_t>();
+  const uint8_t* d_in;
+  if (T.d_in_ext) d_in = T.d_in_ext + in_base;
+  else { reserve_io(d.in, std::max<uint64_t>(in_total, 16), d.arena); d_in = d.in.as<uint8_t>(); }
+  uint8_t* d_work = nullptr;  // pre-processed copy when the transform must not touch the caller's data
+  if (pre == 4 && T.d_in_ext) { reserve_io(d.work, std::max<uint64_t>(in_total, 16), d.arena); d_work = d.work.as<uint8_t>(); }
+  reserve_io(d.slots, std::max<uint64_t>(slots_total, 16), d.arena);
+  uint8_t* d_out = T.d_out_ext;
+  if (!d_out) { reserve_io(d.out, std::max<uint64_t>(slots_total, 16), d.arena); d_out = d.out.as<uint8_t>(); }
+  const uint64_t d_out_cap = T.d_out_ext ? T.d_out_cap : d.out.cap;
+
+  // ---- launch geometry: arenas take what is left ----
+  Launch L;
+  if (M.hdr.n) {
+    const uint64_t fr = free_device_memory() + d.arena.cap;
+    const uint64_t reserve = 512ull << 20;
+    plan_launch(d, M.hdr, false, nb, fr > reserve ? fr - reserve : 0, ctx->max_resident, L);
+    d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
+  } else {
+    plan_launch(d, M.hdr, false, nb, 1ull << 30, ctx->max_resident, L);
+    d.arena.reserve(std::max<uint64_t>((uint64_t)L.resident * L.plan->arena_bytes, 4096));
+  }
+  d.plan.reserve(sizeof(Plan));
+  CU(cudaMemcpyAsync(d.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
+                     cudaMemcpyHostToDevice, s));
+
+  // ---- uploads ----
+  d.t_h2d.start(s);
+  auto up = [&](uint64_t o, const void* src, uint64_t bytes) {
+    if (bytes) CU(cudaMemcpyAsync(meta + o, src, bytes, cudaMemcpyHostToDevice, s));
+  };
+  up(o_jobs, jobs.data(), sizeof(EncJob) * nb);
+  up(o_slot, slot_off.data(), 8ull * (nb + 1));
+  up(o_rel, rel_off.data(), 8ull * nb);
+  up(o_len, lens.data(), 4ull * nb);
+  up(o_poff, prefix_off.data(), 4ull * (nb + 1));
+  up(o_prefix, prefix.data(), prefix.size());
+  up(o_pre, preamble.data(), preamble.size());
+  CU(cudaMemsetAsync(meta + o_queue, 0, 256, s));
+  if (!T.d_in_ext && in_total) {
+    CU(cudaMemcpyAsync(d.in.p, T.h_in + in_base, in_total, cudaMemcpyHostToDevice, s));
+    d.stats.h2d_bytes = in_total;
+  }
+  d.t_h2d.stop(s);
+
+  // ---- kernels ----
+  d.t_kern.start(s);
+  uint32_t launches = 0;
+  if (T.dosha1) {
+    CU(launch_sha1(d_in, (const uint64_t*)(meta + o_rel), (const uint32_t*)(meta + o_len), nb, meta + o_dig, s));
+    ++launches;
+  }
+  const uint8_t* d_coded_in = d_in;
+  if (pre == 4) {  // E8E9 after the checksum, LibZPAQ.cs:307-310
+    uint8_t* tgt = d_work ? d_work : const_cast<uint8_t*>(d_in);
+    if (d_work) CU(cudaMemcpyAsync(d_work, d_in, in_total, cudaMemcpyDeviceToDevice, s));
+    CU(launch_e8e9(tgt, (const uint64_t*)(meta + o_rel), (const uint32_t*)(meta + o_len), nb, s));
+    d_coded_in = tgt;
+    ++launches;
+  }
+  CodecParams P{};
+  P.plan = d.plan.as<Plan>();
+  P.tab = d.d_tab;
+  P.arenas = d.arena.as<uint8_t>();
+  P.arena_stride = L.plan->arena_bytes;
+  P.in = d_coded_in;
+  P.preamble = meta + o_pre;
+  P.out = d.slots.as<uint8_t>();
+  P.ejobs = (const EncJob*)(meta + o_jobs);
+  P.results = (BlockResult*)(meta + o_res);
+  P.njobs = nb;
+  P.resident = L.resident;
+  P.queue = (uint32_t*)(meta + o_queue);
+  P.sm = L.sm;
+  d.t_codec.start(s);
+  CU(launch_encode(P, L.geom, s));
+  d.t_codec.stop(s);
+  ++launches;
+
+  FinishParams F{};
+  F.slots = d.slots.as<uint8_t>();
+  F.slot_off = (const uint64_t*)(meta + o_slot);
+  F.prefix = meta + o_prefix;
+  F.prefix_off = (const uint32_t*)(meta + o_poff);
+  F.results = (const BlockResult*)(meta + o_res);
+  F.digests = T.dosha1 ? meta + o_dig : nullptr;
+  F.frame_len = (uint64_t*)(meta + o_flen);
+  F.nb = nb;
+  CU(launch_finish(F, s));
+  CU(launch_scan((const uint64_t*)(meta + o_flen), (uint64_t*)(meta + o_foff), nb, s));
+  CU(launch_gather(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint64_t*)(meta + o_flen), d_out,
+                   (const uint64_t*)(meta + o_foff), d_out_cap, nb, max_frame, s));
+  launches += 3;
+  d.t_kern.stop(s);
+
+  // ---- results ----
+  std::vector<BlockResult> res(nb);
+  T.frame_off.assign(nb + 1, 0);
+  d.t_d2h.start(s);
+  CU(cudaMemcpyAsync(res.data(), meta + o_res, sizeof(BlockResult) * nb, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(T.frame_off.data(), meta + o_foff, 8ull * (nb + 1), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (uint32_t i = 0; i < nb; ++i) {
+    if (res[i].status == ZPQ_BLOCK_OVERFLOW) throw Failure(ZPQ_E_OUTPUT, "coded block " + std::to_string(T.first + i) + " outgrew its slot");
+    if (res[i].status != ZPQ_BLOCK_OK) throw Failure(ZPQ_E_CONFIG, "ZPAQL execution error while coding block " + std::to_string(T.first + i));
+  }
+  const uint64_t total = T.frame_off[nb];
+  if (total > d_out_cap) throw Failure(ZPQ_E_OUTPUT, "output buffer too small");
+  if (h_out) {
+    if (total > h_out_cap) throw Failure(ZPQ_E_OUTPUT, "output buffer too small");
+    CU(cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, s));
+    d.stats.d2h_bytes = total;
+  }
+  d.t_d2h.stop(s);
+  d.t_all.stop(s);
+  CU(cudaStreamSynchronize(s));
+  d.stats.h2d_ms = d.t_h2d.ms(); d.stats.kernel_ms = d.t_kern.ms(); d.stats.d2h_ms = d.t_d2h.ms();
+  d.stats.total_ms = d.t_all.ms(); d.stats.codec_kernel_ms = d.t_codec.ms();
+  d.stats.launches = launches; d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
+  return total;
+}
+
+// Split [0, nb) among the context's devices by input bytes, run them concurrently, and lay the
+// results out in block order.
+void compress_model(zpq_ctx* ctx, const Model& M, const uint8_t* in, const uint64_t* in_off, uint32_t first, uint32_t nb,
+                    const std::vector<std::string>& filenames, const std::vector<std::string>& comments, bool dosha1,
+                    bool with_tag, uint8_t* out, uint64_t out_cap, uint64_t out_base, uint64_t* out_off) {
+  const size_t nd = std::min<size_t>(ctx->devs.size(), std::max<uint32_t>(nb, 1));
+  std::vector<uint32_t> cut(nd + 1, first);
+  {
+    const uint64_t total = in_off[first + nb] - in_off[first];
+    uint32_t b = first;
+    for (size_t k = 1; k < nd; ++k) {
+      const uint64_t target = in_off[first] + total * k / nd;
+      while (b < first + nb && in_off[b] < target) ++b;
+      cut[k] = b;
+    }
+    cut[nd] = first + nb;
+  }
+  if (nd == 1) {
+    CompressTask T;
+    T.model = &M; T.h_in = in; T.in_off = in_off; T.first = first; T.count = nb;
+    T.filenames = filenames; T.comments = comments; T.dosha1 = dosha1; T.with_tag = with_tag;
+    if (out_base > out_cap) throw Failure(ZPQ_E_OUTPUT, "output buffer too small");
+    compress_on_device(ctx, ctx->devs[0], T, out + out_base, out_cap - out_base);
+    for (uint32_t i = 0; i <= nb; ++i) out_off[first + i] = out_base + T.frame_off[i];
+    return;
+  }
+  // several devices: each compresses its range into its own device buffer, then the host copies
+  // the pieces to their final place once all sizes are known
+  std::vector<CompressTask> tasks(nd);
+  std::vector<std::string> errs(nd);
+  std::vector<int> codes(nd, 0);
+  std::vector<std::thread> th;
+  for (size_t k = 0; k < nd; ++k) {
+    CompressTask& T = tasks[k];
+    T.model = &M; T.h_in = in; T.in_off = in_off; T.first = cut[k]; T.count = cut[k + 1] - cut[k];
+    T.dosha1 = dosha1; T.with_tag = with_tag;
+    for (uint32_t i = cut[k]; i < cut[k + 1]; ++i) {
+      T.filenames.push_back(filenames.size() > i - first ? filenames[i - first] : std::string());
+      T.comments.push_back(comments.size() > i - first ? comments[i - first] : std::string());
+    }
+    th.emplace_back([&, k]() {
+      try {
+        if (tasks[k].count) compress_on_device(ctx, ctx->devs[k], tasks[k], nullptr, 0);
+        else tasks[k].frame_off.assign(1, 0);
+      } catch (const Failure& f) { codes[k] = f.code; errs[k] = f.what(); }
+      catch (const std::exception& e) { codes[k] = ZPQ_E_CUDA; errs[k] = e.what(); }
+    });
+  }
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < nd; ++k) if (codes[k]) throw Failure(codes[k], errs[k]);
+  uint64_t base = out_base;
+  for (size_t k = 0; k < nd; ++k) {
+    const CompressTask& T = tasks[k];
+    const uint64_t total = T.frame_off[T.count];
+    if (base + total > out_cap) throw Failure(ZPQ_E_OUTPUT, "output buffer too small");
+    Device& d = ctx->devs[k];
+    CU(cudaSetDevice(d.id));
+    if (total) CU(cudaMemcpyAsync(out + base, d.out.p, total, cudaMemcpyDeviceToHost, d.stream));
+    for (uint32_t i = 0; i <= T.count; ++i) out_off[T.first + i] = base + T.frame_off[i];
+    base += total;
+  }
+  for (size_t k = 0; k < nd; ++k) { CU(cudaSetDevice(ctx->devs[k].id)); CU(cudaStreamSynchronize(ctx->devs[k].stream)); }
+}
+
+void model_from_header_bytes(const uint8_t* hdr, uint64_t hdr_len, const uint8_t* pcomp, uint64_t pcomp_len, const int* args9,
+                             Model& M) {
+  if (!hdr || hdr_len < 8) throw Failure(ZPQ_E_ARG, "missing block header");
+  size_t used = parse_header(hdr, hdr_len, M.hdr);
+  if (used != hdr_len) throw Failure(ZPQ_E_ARG, "block header length mismatch");
+  M.pcomp.assign(pcomp, pcomp + (pcomp ? pcomp_len : 0));
+  if (M.pcomp.size() > 65535) throw Failure(ZPQ_E_ARG, "PCOMP program too long");
+  for (int i = 0; i < 9; ++i) M.args[i] = args9 ? args9[i] : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decompression
+// ------------------------------------------------------------------------------------------
+struct DecBlock {
+  BlockRef ref;
+  uint64_t start;      // absolute offset of the block in `in`
+  uint64_t cap;        // output slot capacity
+  bool hinted;
+};
+
+void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, uint8_t* out, uint64_t out_cap,
+                    uint64_t* out_off, uint8_t* sha1_status, uint8_t* block_status) {
+  Device& d = ctx->devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t s = d.stream;
+  d.stats = zpq_stats{};
+  d.t_all.start(s);
+  // ---- parse framing on the host ----
+  std::vector<DecBlock> blocks(nb);
+  std::vector<uint8_t> bstat(nb, ZPQ_BLOCK_OK);
+  bool any_corrupt = false;
+  std::string first_err;
+  for (uint32_t i = 0; i < nb; ++i) {
+    DecBlock& b = blocks[i];
+    b.start = in_off[i];
+    try {
+      parse_block(in + in_off[i], in_off[i + 1] - in_off[i], b.ref);
+    } catch (const Failure& f) {
+      bstat[i] = ZPQ_BLOCK_CORRUPT; any_corrupt = true;
+      if (first_err.empty()) first_err = "block " + std::to_string(i) + ": " + f.what();
+      b.ref.segs.clear();
+    }
+    uint64_t cap = 0; b.hinted = true;
+    for (const SegmentRef& sg : b.ref.segs) {
+      if (sg.size_hint >= 0) cap += (uint64_t)sg.size_hint;
+      else { b.hinted = false; cap += sg.data_len * 16 + (1 << 20); }
+    }
+    b.cap = cap + 16;
+  }
+  const uint64_t in_base = in_off[0], in_total = in_off[nb] - in_off[0];
+  reserve_io(d.in, std::max<uint64_t>(in_total, 16), d.arena);
+  d.t_h2d.start(s);
+  if (in_total) CU(cudaMemcpyAsync(d.in.p, in + in_base, in_total, cudaMemcpyHostToDevice, s));
+  d.stats.h2d_bytes = in_total;
+  d.t_h2d.stop(s);
+
+  std::vector<BlockResult> res(nb);
+  std::vector<uint32_t> pending;
+  for (uint32_t i = 0; i < nb; ++i) if (bstat[i] == ZPQ_BLOCK_OK) pending.push_back(i);
+  std::vector<uint64_t> slot_off(nb + 1, 0);
+  std::vector<uint8_t> sha(nb, 0);
+  uint32_t launches = 0;
+  double codec_ms = 0;
+  d.t_kern.start(s);
+
+  for (int attempt = 0; attempt < 4 && !pending.empty(); ++attempt) {
+    // slots for the pending blocks
+    uint64_t slots_total = 0;
+    for (uint32_t i : pending) { slot_off[i] = slots_total; slots_total = align_up(slots_total + blocks[i].cap, 16); }
+    reserve_io(d.slots, std::max<uint64_t>(slots_total, 16), d.arena);
+    // group by header bytes
+    std::map<Bytes, std::vector<uint32_t>> groups;
+    for (uint32_t i : pending) groups[blocks[i].ref.hdr.wire].push_back(i);
+    std::vector<uint64_t> seg_end_all;  // per pending block & segment: output position at segment end
+    for (auto& g : groups) {
+      const std::vector<uint32_t>& ids = g.second;
+      const Header& hdr = blocks[ids[0]].ref.hdr;
+      std::vector<DecJob> jobs(ids.size());
+      std::vector<DecSeg> segs;
+      for (size_t k = 0; k < ids.size(); ++k) {
+        const DecBlock& b = blocks[ids[k]];
+        jobs[k].seg_first = (uint32_t)segs.size();
+        jobs[k].seg_count = (uint32_t)b.ref.segs.size();
+        jobs[k].out_off = slot_off[ids[k]];
+        jobs[k].out_cap = b.cap;
+        for (const SegmentRef& sg : b.ref.segs) segs.push_back(DecSeg{b.start - in_base + sg.data_off, sg.data_len});
+      }
+      uint64_t mo = 0;
+      auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
+      const uint64_t o_jobs = place(sizeof(DecJob) * jobs.size()), o_segs = place(sizeof(DecSeg) * std::max<size_t>(segs.size(), 1)),
+                     o_res = place(sizeof(BlockResult) * jobs.size()), o_queue = place(256);
+      d.meta.reserve(mo);
+      uint8_t* meta = d.meta.as<uint8_t>();
+      Launch L;
+      const uint64_t fr = free_device_memory() + d.arena.cap;
+      const uint64_t reserve = 512ull << 20;
+      plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L);
+      d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
+      d.plan.reserve(sizeof(Plan));
+      CU(cudaMemcpyAsync(d.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
+                         cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(meta + o_jobs, jobs.data(), sizeof(DecJob) * jobs.size(), cudaMemcpyHostToDevice, s));
+      if (!segs.empty()) CU(cudaMemcpyAsync(meta + o_segs, segs.data(), sizeof(DecSeg) * segs.size(), cudaMemcpyHostToDevice, s));
+      CU(cudaMemsetAsync(meta + o_queue, 0, 256, s));
+      CodecParams P{};
+      P.plan = d.plan.as<Plan>(); P.tab = d.d_tab;
+      P.arenas = d.arena.as<uint8_t>(); P.arena_stride = L.plan->arena_bytes;
+      P.in = d.in.as<uint8_t>(); P.out = d.slots.as<uint8_t>();
+      P.djobs = (const DecJob*)(meta + o_jobs); P.segs = (const DecSeg*)(meta + o_segs);
+      P.results = (BlockResult*)(meta + o_res);
+      P.njobs = (uint32_t)jobs.size(); P.resident = L.resident; P.queue = (uint32_t*)(meta + o_queue); P.sm = L.sm;
+      d.t_codec.start(s);
+      CU(launch_decode(P, L.geom, s));
+      d.t_codec.stop(s);
+      ++launches;
+      std::vector<BlockResult> r(jobs.size());
+      CU(cudaMemcpyAsync(r.data(), meta + o_res, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      codec_ms += d.t_codec.ms();
+      d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
+      for (size_t k = 0; k < ids.size(); ++k) res[ids[k]] = r[k];
+    }
+    // an unhinted block that outgrew its slot gets a larger one and the batch is decoded again
+    bool again = false;
+    for (uint32_t i : pending)
+      if (res[i].status == ZPQ_BLOCK_OVERFLOW && !blocks[i].hinted) { blocks[i].cap *= 8; again = true; }
+    if (!again) break;
+  }
+  // ---- SHA-1 of every block's output when a checksum is stored (single-segment blocks) ----
+  std::vector<uint64_t> lens(nb, 0);
+  for (uint32_t i = 0; i < nb; ++i) {
+    if (bstat[i] != ZPQ_BLOCK_OK) continue;
+    bstat[i] = (uint8_t)res[i].status;
+    if (res[i].status == ZPQ_BLOCK_OK) lens[i] = res[i].out_len;
+    else { any_corrupt = true; if (first_err.empty()) first_err = "block " + std::to_string(i) + " failed to decode (status " + std::to_string(res[i].status) + ")"; }
+  }
+  {
+    uint64_t mo = 0;
+    auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
+    const uint64_t o_slot = place(8ull * (nb + 1)), o_len64 = place(8ull * nb), o_len32 = place(4ull * nb),
+                   o_foff = place(8ull * (nb + 1)), o_dig = place(20ull * nb);
+    d.meta.reserve(mo);
+    uint8_t* meta = d.meta.as<uint8_t>();
+    std::vector<uint32_t> len32(nb);
+    uint64_t max_len = 0;
+    for (uint32_t i = 0; i < nb; ++i) { len32[i] = (uint32_t)lens[i]; max_len = std::max(max_len, lens[i]); }
+    CU(cudaMemcpyAsync(meta + o_slot, slot_off.data(), 8ull * (nb + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(meta + o_len64, lens.data(), 8ull * nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(meta + o_len32, len32.data(), 4ull * nb, cudaMemcpyHostToDevice, s));
+    CU(launch_sha1(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint32_t*)(meta + o_len32), nb, meta + o_dig, s));
+    CU(launch_scan((const uint64_t*)(meta + o_len64), (uint64_t*)(meta + o_foff), nb, s));
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nb; ++i) total += lens[i];
+    reserve_io(d.out, std::max<uint64_t>(total, 16), d.arena);
+    CU(launch_gather(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint64_t*)(meta + o_len64),
+                     d.out.as<uint8_t>(), (const uint64_t*)(meta + o_foff), d.out.cap, nb, max_len, s));
+    launches += 3;
+    d.t_kern.stop(s);
+    std::vector<uint8_t> dig(20ull * nb);
+    d.t_d2h.start(s);
+    CU(cudaMemcpyAsync(dig.data(), meta + o_dig, 20ull * nb, cudaMemcpyDeviceToHost, s));
+    if (total > out_cap) { out_off[nb] = total; throw Failure(ZPQ_E_OUTPUT, "output buffer too small"); }
+    if (total) CU(cudaMemcpyAsync(out, d.out.p, total, cudaMemcpyDeviceToHost, s));
+    d.stats.d2h_bytes = total;
+    d.t_d2h.stop(s);
+    d.t_all.stop(s);
+    CU(cudaStreamSynchronize(s));
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < nb; ++i) {
+      out_off[i] = acc; acc += lens[i];
+      uint8_t st = 0;
+      const auto& segs = blocks[i].ref.segs;
+      if (bstat[i] == ZPQ_BLOCK_OK && segs.size() == 1 && segs[0].has_sha1)
+        st = memcmp(segs[0].sha1, &dig[20ull * i], 20) == 0 ? 1 : 2;
+      sha[i] = st;
+    }
+    out_off[nb] = acc;
+  }
+  if (sha1_status) memcpy(sha1_status, sha.data(), nb);
+  if (block_status) memcpy(block_status, bstat.data(), nb);
+  d.stats.h2d_ms = d.t_h2d.ms(); d.stats.kernel_ms = d.t_kern.ms(); d.stats.d2h_ms = d.t_d2h.ms();
+  d.stats.total_ms = d.t_all.ms(); d.stats.codec_kernel_ms = codec_ms; d.stats.launches = launches;
+  if (any_corrupt) throw Failure(ZPQ_E_CORRUPT, first_err);
+}
+
+template <class F> int guarded(zpq_ctx* ctx, F&& f) {
+  try { f(); return ZPQ_OK; }
+  catch (const Failure& e) { if (ctx) ctx->err = e.what(); else { std::lock_guard<std::mutex> g(g_create_mutex); g_create_error = e.what(); } return e.code; }
+  catch (const std::bad_alloc&) { if (ctx) ctx->err = "out of host memory"; return ZPQ_E_NOMEM; }
+  catch (const std::exception& e) { if (ctx) ctx->err = e.what(); return ZPQ_E_CUDA; }
+}
+
+int64_t copy_out(const std::string& s, char* out, uint64_t cap) {
+  if (out && cap) {
+    const size_t k = std::min<size_t>(s.size(), cap - 1);
+    memcpy(out, s.data(), k);
+    out[k] = 0;
+  }
+  return (int64_t)s.size();
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char* zpq_version(void) { return "zpaqb200 0.1 sm_100a"; }
+
+int zpq_create(const int* device_ids, int ndev, zpq_ctx** out) {
+  if (!out) return ZPQ_E_ARG;
+  *out = nullptr;
+  std::unique_ptr<zpq_ctx> ctx(new zpq_ctx);
+  int rc = guarded(nullptr, [&]() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1)
+      throw Failure(ZPQ_E_CUDA, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    std::vector<int> ids;
+    if (ndev <= 0) { int cur = 0; CU(cudaGetDevice(&cur)); ids.push_back(cur); }
+    else for (int i = 0; i < ndev; ++i) ids.push_back(device_ids ? device_ids[i] : i);
+    for (int id : ids) if (id < 0 || id >= count) throw Failure(ZPQ_E_ARG, "device id out of range");
+    ctx->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) ctx->devs[i].init(ids[i]);
+  });
+  if (rc != ZPQ_OK) { for (auto& d : ctx->devs) d.fini(); return rc; }
+  *out = ctx.release();
+  return ZPQ_OK;
+}
+
+void zpq_destroy(zpq_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& d : ctx->devs) d.fini();
+  delete ctx;
+}
+
+const char* zpq_last_error(zpq_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> g(g_create_mutex);
+  return g_create_error.c_str();
+}
+
+int zpq_set_stream(zpq_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return ZPQ_E_ARG;
+  Device& d = ctx->devs[0];
+  d.stream = cuda_stream ? (cudaStream_t)cuda_stream : d.own;
+  return ZPQ_OK;
+}
+
+int zpq_set_max_resident(zpq_ctx* ctx, uint32_t max_blocks) {
+  if (!ctx) return ZPQ_E_ARG;
+  ctx->max_resident = max_blocks;
+  return ZPQ_OK;
+}
+
+int64_t zpq_make_config(const char* method, int* args9, char* text, uint64_t text_cap) {
+  if (!method || !args9) return ZPQ_E_ARG;
+  std::string r;
+  int rc = guarded(nullptr, [&]() { r = make_config(method, args9); });
+  return rc ? rc : copy_out(r, text, text_cap);
+}
+
+int64_t zpq_expand_method(const char* method, const uint8_t* block, uint64_t n, char* out, uint64_t cap) {
+  if (!method || (!block && n)) return ZPQ_E_ARG;
+  std::string r;
+  int rc = guarded(nullptr, [&]() { r = expand_method(method, block, n); });
+  return rc ? rc : copy_out(r, out, cap);
+}
+
+int zpq_compile_config(const char* config, const int* args9, uint8_t* hdr, uint64_t hdr_cap, uint64_t* hdr_len,
+                       uint8_t* pcomp, uint64_t pcomp_cap, uint64_t* pcomp_len) {
+  if (!config || !hdr_len || !pcomp_len) return ZPQ_E_ARG;
+  return guarded(nullptr, [&]() {
+    Bytes h, p;
+    compile_config(config, args9, h, p, nullptr);
+    *hdr_len = h.size(); *pcomp_len = p.size();
+    if (h.size() > hdr_cap || p.size() > pcomp_cap) throw Failure(ZPQ_E_OUTPUT, "buffer too small");
+    if (hdr) memcpy(hdr, h.data(), h.size());
+    if (pcomp && !p.empty()) memcpy(pcomp, p.data(), p.size());
+  });
+}
+
+int64_t zpq_builtin_model(int level, uint8_t* hdr, uint64_t hdr_cap) {
+  Bytes h;
+  int rc = guarded(nullptr, [&]() { builtin_model(level, h); });
+  if (rc) return rc;
+  if (hdr) { if (h.size() > hdr_cap) return ZPQ_E_OUTPUT; memcpy(hdr, h.data(), h.size()); }
+  return (int64_t)h.size();
+}
+
+double zpq_block_memory(const uint8_t* hdr, uint64_t hdr_len) {
+  double v = -1;
+  guarded(nullptr, [&]() { Header h; parse_header(hdr, hdr_len, h); v = header_memory(h); });
+  return v;
+}
+
+int64_t zpq_device_state_bytes(const uint8_t* hdr, uint64_t hdr_len, int for_decode) {
+  int64_t v = -1;
+  int rc = guarded(nullptr, [&]() {
+    Header h; parse_header(hdr, hdr_len, h);
+    std::unique_ptr<Plan> p(new Plan);
+    build_plan(h, for_decode != 0, 48 * 1024, *p);
+    v = (int64_t)p->arena_bytes;
+  });
+  return rc ? rc : v;
+}
+
+int zpq_compress_blocks_model(zpq_ctx* ctx, const uint8_t* hdr, uint64_t hdr_len, const uint8_t* pcomp, uint64_t pcomp_len,
+                              const int* args9, const uint8_t* in, const uint64_t* in_off, uint32_t nb,
+                              const char* filename0, const char* comment0, int dosha1, int with_tag, uint8_t* out,
+                              uint64_t out_cap, uint64_t* out_off) {
+  if (!ctx || !in_off || !out_off || (!in && nb && in_off[nb] > in_off[0]) || !out) return ZPQ_E_ARG;
+  return guarded(ctx, [&]() {
+    out_off[0] = 0;
+    if (!nb) return;
+    Model M;
+    model_from_header_bytes(hdr, hdr_len, pcomp, pcomp_len, args9, M);
+    std::vector<std::string> fn(1, filename0 ? filename0 : ""), cm(1, comment0 ? comment0 : "");
+    compress_model(ctx, M, in, in_off, 0, nb, fn, cm, dosha1 != 0, with_tag != 0, out, out_cap, 0, out_off);
+  });
+}
+
+int zpq_compress_blocks_level(zpq_ctx* ctx, int level, const uint8_t* in, const uint64_t* in_off, uint32_t nb,
+                              const char* filename0, const char* comment0, int dosha1, int with_tag, uint8_t* out,
+                              uint64_t out_cap, uint64_t* out_off) {
+  if (!ctx) return ZPQ_E_ARG;
+  Bytes h;
+  int rc = guarded(ctx, [&]() { builtin_model(level, h); });
+  if (rc) return rc;
+  return zpq_compress_blocks_model(ctx, h.data(), h.size(), nullptr, 0, nullptr, in, in_off, nb, filename0, comment0, dosha1,
+                                   with_tag, out, out_cap, out_off);
+}
+
+int zpq_compress_blocks(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, const char* method,
+                        const char* filename0, const char* comment0, int dosha1, uint8_t* out, uint64_t out_cap,
+                        uint64_t* out_off) {
+  if (!ctx || !in_off || !out_off || !method || !out || (!in && nb && in_off[nb] > in_off[0])) return ZPQ_E_ARG;
+  return guarded(ctx, [&]() {
+    out_off[0] = 0;
+    // derive each block's model (LibZPAQ.cs:128-300); consecutive blocks with identical models
+    // form one device batch
+    uint32_t i = 0;
+    uint64_t base = 0;
+    while (i < nb) {
+      auto derive = [&](uint32_t b, Model& M) {
+        const uint64_t n = in_off[b + 1] - in_off[b];
+        std::string x = expand_method(method, in + in_off[b], n);
+        std::string cfg = make_config(x, M.args);
+        Bytes h;
+        compile_config(cfg, M.args, h, M.pcomp, nullptr);
+        parse_header(h.data(), h.size(), M.hdr);
+      };
+      Model M;
+      derive(i, M);
+      uint32_t j = i + 1;
+      for (; j < nb; ++j) {
+        Model N;
+        derive(j, N);
+        if (N.hdr.wire != M.hdr.wire || N.pcomp != M.pcomp || memcmp(N.args, M.args, sizeof(M.args)) != 0) break;
+      }
+      std::vector<std::string> fn, cm;
+      for (uint32_t b = i; b < j; ++b) {
+        const uint64_t n = in_off[b + 1] - in_off[b];
+        fn.push_back(b == 0 && filename0 ? filename0 : "");
+        std::string c = std::to_string(n);                       // LibZPAQ.cs:298-299
+        if (b == 0 && comment0 && *comment0) c += std::string(" ") + comment0;
+        cm.push_back(c);
+      }
+      compress_model(ctx, M, in, in_off, i, j - i, fn, cm, dosha1 != 0, true, out, out_cap, base, out_off);
+      base = out_off[j];
+      i = j;
+    }
+  });
+}
+
+int zpq_compress_blocks_model_dev(zpq_ctx* ctx, const uint8_t* hdr, uint64_t hdr_len, const uint8_t* pcomp, uint64_t pcomp_len,
+                                  const int* args9, const uint8_t* d_in, const uint64_t* h_in_off, uint32_t nb, int dosha1,
+                                  int with_tag, uint8_t* d_out, uint64_t out_cap, uint64_t* h_out_off) {
+  if (!ctx || !d_in || !h_in_off || !d_out || !h_out_off) return ZPQ_E_ARG;
+  return guarded(ctx, [&]() {
+    h_out_off[0] = 0;
+    if (!nb) return;
+    Model M;
+    model_from_header_bytes(hdr, hdr_len, pcomp, pcomp_len, args9, M);
+    CompressTask T;
+    T.model = &M; T.d_in_ext = d_in; T.in_off = h_in_off; T.first = 0; T.count = nb;
+    T.dosha1 = dosha1 != 0; T.with_tag = with_tag != 0; T.d_out_ext = d_out; T.d_out_cap = out_cap;
+    compress_on_device(ctx, ctx->devs[0], T, nullptr, 0);
+    for (uint32_t i = 0; i <= nb; ++i) h_out_off[i] = T.frame_off[i];
+  });
+}
+
+int64_t zpq_find_blocks(const uint8_t* archive, uint64_t n, uint64_t* offsets, uint64_t max_blocks) {
+  int64_t r = 0;
+  int rc = guarded(nullptr, [&]() { r = find_blocks(archive, n, offsets, max_blocks); });
+  return rc ? rc : r;
+}
+
+int64_t zpq_decompressed_bound(const uint8_t* in, const uint64_t* in_off, uint32_t nb) {
+  int64_t total = 0;
+  int rc = guarded(nullptr, [&]() {
+    for (uint32_t i = 0; i < nb; ++i) {
+      BlockRef b;
+      parse_block(in + in_off[i], in_off[i + 1] - in_off[i], b);
+      for (const SegmentRef& s : b.segs) total += s.size_hint >= 0 ? s.size_hint : (int64_t)(s.data_len * 64 + 65536);
+      total += 16;
+    }
+  });
+  return rc ? rc : total;
+}
+
+int zpq_decompress_blocks(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, uint8_t* out, uint64_t out_cap,
+                          uint64_t* out_off, uint8_t* sha1_status, uint8_t* block_status) {
+  if (!ctx || !in || !in_off || !out_off || (!out && out_cap)) return ZPQ_E_ARG;
+  return guarded(ctx, [&]() {
+    out_off[0] = 0;
+    if (!nb) return;
+    decompress_all(ctx, in, in_off, nb, out, out_cap, out_off, sha1_status, block_status);
+  });
+}
+
+int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out) {
+  if (!ctx || !out) return ZPQ_E_ARG;
+  *out = ctx->devs[0].stats;
+  return ZPQ_OK;
+}
+
+}  // extern "C"

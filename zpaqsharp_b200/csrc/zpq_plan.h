@@ -1,0 +1,104 @@
+// zpq_plan.h -- structures shared by the host scheduler and the sm_100a kernels.
+//
+// A "plan" is the device-side form of one ZPAQ block header (ZPAQL.cs:112-156 layout): the
+// component list of Predictor.init (Predictor.cs:84-171) flattened into fixed-size descriptors
+// with table offsets inside a per-block state arena, an evaluation schedule (components grouped
+// by dependency level so that one warp evaluates a level across its lanes), the table
+// initialisation list and the HCOMP bytecode.
+#pragma once
+#include <stdint.h>
+
+namespace zpq {
+
+enum CompType : uint8_t { C_NONE = 0, C_CONS, C_CM, C_ICM, C_MATCH, C_AVG, C_MIX2, C_MIX, C_ISSE, C_SSE };
+
+constexpr int kMaxComp = 255;
+constexpr uint32_t kNoSmem = 0xFFFFFFFFu;
+
+// One model component.  `a[]` are the descriptor bytes after the type (Component.cs:27-43).
+struct CompDesc {
+  uint8_t type;
+  uint8_t a[5];
+  uint8_t level;       // dependency depth: 0 = reads no other prediction
+  uint8_t coop;        // 1 = evaluated by the whole warp (MIX)
+  uint32_t mask;       // index mask of the primary table (entries - 1), or context-count mask for MIX/MIX2
+  uint32_t mask2;      // MATCH: buffer mask
+  uint64_t tab;        // arena byte offset of the primary table (cm / ht / a16 / MATCH index)
+  uint64_t tab2;       // arena byte offset of the secondary table (ICM/ISSE cm when not in smem; MATCH buffer)
+  uint32_t smem_cm;    // byte offset of the ICM/ISSE cm table in the warp's shared slice, or kNoSmem
+  uint32_t pad;
+};
+static_assert(sizeof(CompDesc) == 40, "CompDesc layout");
+
+// Table fill executed by the owning warp when it starts a block (Predictor.cs:96-165).
+struct InitOp {
+  uint64_t dst;        // arena byte offset, or shared-slice offset when to_smem
+  uint64_t bytes;      // multiple of 16
+  uint32_t value;      // fill word (kind 0) / SSE start count (kind 3)
+  uint8_t kind;        // 0 = constant word, 1 = ICM cm template, 2 = ISSE cm template, 3 = SSE pattern
+  uint8_t to_smem;
+  uint16_t pad;
+};
+
+// One step of the per-bit prediction schedule.
+struct Step {
+  uint16_t first;      // index into order[]
+  uint8_t count;       // components in this step (<= 32); lane l takes order[first+l]
+  uint8_t coop;        // 1 = a single cooperative component
+};
+
+struct Plan {
+  int32_t n;                    // components
+  int32_t hh, hm, ph, pm;       // log2 sizes of H, M (HCOMP) and H, M (PCOMP)
+  int32_t nsteps, nupd, ninit;
+  int32_t hcomp_len;            // bytes of HCOMP program incl. END
+  uint32_t smem_warp_bytes;     // shared memory slice per resident block
+  uint32_t smem_p, smem_st, smem_h, smem_cm;  // slice offsets: p[], state[], H (or kNoSmem), cm tables
+  uint64_t arena_bytes;         // per resident block
+  uint64_t off_h, off_m, off_r; // HCOMP H (if not in smem), M, R[256]
+  uint64_t off_ph, off_pm, off_pr, off_pcode;  // decode only: PCOMP H, M, R and program (<= 64 KB)
+  CompDesc comp[kMaxComp];
+  uint8_t order[kMaxComp];      // components sorted by (level, coop)
+  uint8_t upd[kMaxComp];        // lane-parallel update list (non-coop components that learn)
+  Step steps[kMaxComp * 2];
+  InitOp init[kMaxComp * 2 + 8];
+  uint8_t hcomp[65536 + 8];
+};
+
+// Per-block job for the coding kernels.
+struct EncJob {
+  uint64_t in_off;      // into the (pre-processed) input buffer
+  uint32_t in_len;
+  uint32_t pre_len;     // bytes of the preamble buffer to code first (PCOMP preamble, Compressor.cs:177-188)
+  uint64_t out_off;     // into the slot buffer: where coded bytes start
+  uint64_t out_cap;     // coded bytes allowed
+};
+
+struct DecSeg {         // one segment's coded byte range
+  uint64_t in_off;
+  uint64_t in_len;
+};
+struct DecJob {
+  uint32_t seg_first, seg_count;  // into the DecSeg array
+  uint64_t out_off, out_cap;
+};
+
+struct BlockResult {
+  uint64_t out_len;     // coded (encode) or restored (decode) bytes
+  uint32_t status;      // ZPQ_BLOCK_*
+  uint32_t pad;
+};
+
+// Read-only tables, built on the host (Predictor.cs:54-67, StateTable.cs) and copied once.
+struct Tables {
+  int16_t stretch[32768];
+  uint16_t squash[4096];
+  int32_t dt[1024];
+  uint16_t dt2k[256];
+  uint8_t ns[1024];
+  uint32_t icm_init[256];   // cminit(j)                       Predictor.cs:111-112
+  uint32_t isse_init[512];  // {1<<15, clamp512k(stretch(cminit(j)>>8)*1024)}  Predictor.cs:150-155
+  uint32_t sse_init[32];    // squash((j&31)*64-992)<<17       Predictor.cs:163-164
+};
+
+}  // namespace zpq
