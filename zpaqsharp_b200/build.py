@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libzpaqb200.so")
 SOURCES = ["zpq_kernels.cu", "zpq_api.cpp", "zpq_model.cpp", "zpq_frontend.cpp"]
-HEADERS = ["zpq_plan.h", "zpq_device.h", "zpq_host.h", os.path.join("..", "..", "include", "zpaqb200.h")]
+HEADERS = ["zpq_plan.h", "zpq_device.h", "zpq_host.h", "zpq_lane.cuh", os.path.join("..", "..", "include", "zpaqb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-cudart", "static"]

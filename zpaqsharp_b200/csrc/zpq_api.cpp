@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -134,10 +135,13 @@ uint32_t common_smem(const Plan& pl, SmemLayout& L) {
   L.comp = o; o += (uint32_t)align_up((uint64_t)std::max(pl.n, 1) * sizeof(CompDesc), 16);
   L.order = o; o += (uint32_t)align_up(std::max(pl.n, 1), 16);
   L.steps = o; o += (uint32_t)align_up((uint64_t)std::max(pl.nsteps, 1) * sizeof(Step), 16);
+  L.mix = o; o += (uint32_t)align_up((uint64_t)std::max(pl.nmix, 1) * sizeof(MixDesc), 16);
   if (pl.hcomp_len + 8 <= 4096) { L.hcomp = o; o += (uint32_t)align_up(pl.hcomp_len + 8, 16); }
   else L.hcomp = kNoSmem;
   return (uint32_t)align_up(o, 128);
 }
+
+bool force_generic();
 
 void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint64_t mem_for_arenas, uint32_t max_resident,
                  Launch& L) {
@@ -155,7 +159,7 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
     uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
     if ((uint64_t)W * L.plan->smem_warp_bytes <= avail) break;
     uint32_t budget = avail / W;
-    uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64, 128);
+    uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64 + 512, 128);
     if (budget >= minimal) {
       build_plan(hdr, decode, budget & ~127u, *L.plan);
       common = common_smem(*L.plan, L.sm);
@@ -170,9 +174,13 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
   L.sm.slice_bytes = L.plan->smem_warp_bytes;
   L.sm.total = L.sm.slices + W * L.sm.slice_bytes;
   L.geom.warps_per_cta = W;
+  L.geom.lanes = (L.plan->lane_ok && !force_generic()) ? 1u : 0u;
   L.geom.grid = (uint32_t)((resident + W - 1) / W);
   L.resident = (uint32_t)resident;
 }
+
+// ZPQ_FORCE_GENERIC=1 selects the step-scheduled kernels even for small models (test hook).
+bool force_generic() { const char* e = getenv("ZPQ_FORCE_GENERIC"); return e && *e == '1'; }
 
 uint64_t free_device_memory() {
   size_t fr = 0, tot = 0;

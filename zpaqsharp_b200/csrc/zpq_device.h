@@ -10,7 +10,7 @@ namespace zpq {
 
 // Offsets (bytes) of the CTA-common part of dynamic shared memory.
 struct SmemLayout {
-  uint32_t stretch, squash, dt, dt2k, ns, comp, order, steps, hcomp;  // hcomp == kNoSmem: read from the plan
+  uint32_t stretch, squash, dt, dt2k, ns, comp, order, steps, mix, hcomp;  // hcomp == kNoSmem: read from the plan
   uint32_t slices;        // first per-block slice
   uint32_t slice_bytes;   // == plan.smem_warp_bytes
   uint32_t total;         // dynamic shared bytes of the launch
@@ -36,6 +36,7 @@ struct CodecParams {
 
 struct LaunchGeom {
   uint32_t grid, warps_per_cta;
+  uint32_t lanes;   // 1: lane-resident kernels (n <= 32), 0: step-scheduled generic kernels
 };
 
 // Launch wrappers (all asynchronous on `s`).

@@ -43,7 +43,8 @@ struct Shared {
   const uint8_t* order;
   const Step* steps;
   const uint8_t* hcomp;  // shared copy when it fits, else the plan's global copy
-  int n, nsteps, hcomp_len;
+  const MixDesc* mix;
+  int n, nsteps, hcomp_len, nmix, maxlevel;
 };
 
 // Per-block (per-warp) mutable context.
@@ -440,6 +441,9 @@ __device__ void stage_shared(const CodecParams& P, uint8_t* smem, Shared& S) {
     for (int i = threadIdx.x; i < ns; i += blockDim.x) sdst[i] = ssrc[i];
     if (L.hcomp != kNoSmem)
       for (int i = threadIdx.x; i < plan->hcomp_len + 8; i += blockDim.x) smem[L.hcomp + i] = plan->hcomp[i];
+    const uint32_t* msrc = reinterpret_cast<const uint32_t*>(plan->mix);
+    uint32_t* mdst = reinterpret_cast<uint32_t*>(smem + L.mix);
+    for (int i = threadIdx.x; i < plan->nmix * (int)(sizeof(MixDesc) / 4); i += blockDim.x) mdst[i] = msrc[i];
   }
   __syncthreads();
   S.stretch = reinterpret_cast<const int16_t*>(smem + L.stretch);
@@ -451,7 +455,8 @@ __device__ void stage_shared(const CodecParams& P, uint8_t* smem, Shared& S) {
   S.order = smem + L.order;
   S.steps = reinterpret_cast<const Step*>(smem + L.steps);
   S.hcomp = L.hcomp != kNoSmem ? smem + L.hcomp : plan->hcomp;
-  S.n = n; S.nsteps = ns; S.hcomp_len = plan->hcomp_len;
+  S.mix = reinterpret_cast<const MixDesc*>(smem + L.mix);
+  S.n = n; S.nsteps = ns; S.hcomp_len = plan->hcomp_len; S.nmix = plan->nmix; S.maxlevel = plan->maxlevel;
 }
 
 // Reset everything a new block needs (Predictor.init + ZPAQL.inith).
@@ -703,21 +708,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParam
   }
 }
 
-cudaError_t codec_set_smem_limit(uint32_t bytes) {
-  cudaError_t e = cudaFuncSetAttribute(k_zpaq_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_zpaq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
-cudaError_t launch_encode(const CodecParams& p, LaunchGeom g, cudaStream_t s) {
-  k_zpaq_encode<<<g.grid, g.warps_per_cta * 32, p.sm.total, s>>>(p);
-  return cudaGetLastError();
-}
-cudaError_t launch_decode(const CodecParams& p, LaunchGeom g, cudaStream_t s) {
-  k_zpaq_decode<<<g.grid, g.warps_per_cta * 32, p.sm.total, s>>>(p);
-  return cudaGetLastError();
-}
-
 // ------------------------------------------------------------------------------------------
 // SHA-1 (FIPS 180-4), one thread per byte range.  The reference hashes every input block
 // (LibZPAQ.cs:143-155) with a SHA1 class it does not ship; any conforming SHA-1 is identical.
@@ -879,6 +869,33 @@ cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const uin
   if (!nb || !max_len) return cudaSuccess;
   dim3 grid(nb, (unsigned)((max_len + kGatherChunk - 1) / kGatherChunk));
   k_gather<<<grid, 256, 0, s>>>(src, src_off, len, dst, dst_off, dst_cap);
+  return cudaGetLastError();
+}
+
+}  // namespace zpq
+
+#include "zpq_lane.cuh"
+
+namespace zpq {
+
+cudaError_t codec_set_smem_limit(uint32_t bytes) {
+  const void* ks[4] = {(const void*)k_zpaq_encode, (const void*)k_zpaq_decode, (const void*)k_zpaq_encode_lanes,
+                       (const void*)k_zpaq_decode_lanes};
+  for (const void* k : ks) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_encode(const CodecParams& p, LaunchGeom g, cudaStream_t s) {
+  if (g.lanes) k_zpaq_encode_lanes<<<g.grid, g.warps_per_cta * 32, p.sm.total, s>>>(p);
+  else k_zpaq_encode<<<g.grid, g.warps_per_cta * 32, p.sm.total, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_decode(const CodecParams& p, LaunchGeom g, cudaStream_t s) {
+  if (g.lanes) k_zpaq_decode_lanes<<<g.grid, g.warps_per_cta * 32, p.sm.total, s>>>(p);
+  else k_zpaq_decode<<<g.grid, g.warps_per_cta * 32, p.sm.total, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -157,6 +157,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   const int nn = std::max(h.n, 1);
   pl.smem_p = stake(4u * nn);
   pl.smem_st = stake(20u * nn);
+  pl.smem_rows = stake(512);
   const uint64_t hbytes = 4ull << h.hh;
   if (h.n > 0 && hbytes <= 2048 && slice + hbytes <= smem_budget) { pl.smem_h = stake((uint32_t)hbytes); fill(pl.smem_h, hbytes, 0, 0, true); }
   else { pl.smem_h = kNoSmem; pl.off_h = take(hbytes); fill(pl.off_h, hbytes, 0, 0, false); }
@@ -277,6 +278,17 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
       }
   }
   pl.nsteps = ns;
+  pl.maxlevel = maxlevel;
+  pl.nmix = 0;
+  pl.lane_ok = h.n >= 1 && h.n <= 32;
+  for (int i = 0; i < h.n; ++i) {
+    const CompDesc& d = pl.comp[i];
+    if (d.type != C_MIX) continue;
+    if (pl.nmix == kMaxMix) { pl.lane_ok = 0; break; }
+    MixDesc& m = pl.mix[pl.nmix++];
+    m.lane = (uint8_t)i; m.level = d.level; m.j0 = d.a[1]; m.m = d.a[2]; m.rate = d.a[3]; m.cmask = d.a[4];
+    m.pad = 0; m.pad2 = 0; m.mask = d.mask; m.tab = d.tab;
+  }
   for (int i = 0; i < h.n; ++i) {
     const int t = pl.comp[i].type;
     if (t == C_CM || t == C_ICM || t == C_MATCH || t == C_MIX2 || t == C_ISSE || t == C_SSE) pl.upd[nu++] = (uint8_t)i;

@@ -41,11 +41,24 @@ struct InitOp {
 };
 
 // One step of the per-bit prediction schedule.
-struct Step {
+struct alignas(4) Step {
   uint16_t first;      // index into order[]
   uint8_t count;       // components in this step (<= 32); lane l takes order[first+l]
   uint8_t coop;        // 1 = a single cooperative component
 };
+
+// A MIX component as the lane-resident kernel sees it (evaluated by the whole warp).
+struct MixDesc {
+  uint8_t lane;        // component index == owning lane
+  uint8_t level;
+  uint8_t j0, m;       // inputs p[j0 .. j0+m)
+  uint8_t rate, cmask; // learning rate, mask applied to the partial byte c8
+  uint16_t pad;
+  uint32_t mask;       // contexts - 1
+  uint32_t pad2;
+  uint64_t tab;        // arena offset of the weight rows
+};
+constexpr int kMaxMix = 16;
 
 struct Plan {
   int32_t n;                    // components
@@ -57,6 +70,10 @@ struct Plan {
   uint64_t arena_bytes;         // per resident block
   uint64_t off_h, off_m, off_r; // HCOMP H (if not in smem), M, R[256]
   uint64_t off_ph, off_pm, off_pr, off_pcode;  // decode only: PCOMP H, M, R and program (<= 64 KB)
+  int32_t lane_ok;              // 1: n <= 32 and few MIXes -> lane-resident kernel applies
+  int32_t nmix, maxlevel;
+  uint32_t smem_rows;           // slice offset of the 32 x 16-byte hash-row cache
+  MixDesc mix[kMaxMix];
   CompDesc comp[kMaxComp];
   uint8_t order[kMaxComp];      // components sorted by (level, coop)
   uint8_t upd[kMaxComp];        // lane-parallel update list (non-coop components that learn)
