@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native ZPAQ block codec.
+
+Metric (BASELINE.json): compress & decompress MB/s (MB = 10^6 input bytes), method-2 (mid.cfg =
+Compressor.startBlock(2)), 1 MB blocks (1,044,480 B), byte-exact, 1/2/4/8 B200.
+
+A "step" is one pass of the compress hot path over one batch of synthetic mixed text/binary blocks
+(the batch is as many blocks as fit resident on one GPU: one warp per block, ~106 MiB of model
+state per block).  Blocks are independent, so N GPUs = N ranks each coding its own batch (weak
+scaling, no collective on the data path; NCCL is used for the barrier and the max-over-ranks only).
+
+  value     compress MB/s, whole job, inputs and outputs resident in HBM (kernel path only)
+  e2e       the same through the public C ABI with HOST buffers: pinned H2D of every block and
+            D2H of every archive inside the timed region
+  roofline  HBM roofline of the coding kernel from the algorithmic bytes of SURVEY.md 8d
+  cpu_baseline / --impl reference
+            the CPU oracle (a C++ restatement of the reference; ZPAQSharp itself cannot be built,
+            SURVEY.md 8c) timed on the box's host cores on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = (0x100000 << 0) - 4096          # 1,044,480 B  (LibZPAQ.cs:94)
+TOTAL_BLOCKS = 8192                     # the 8 GB stream of BASELINE.json configs[1]
+LEVEL = 2                               # mid.cfg
+ALGO_BYTES_PER_INPUT_BYTE = 950.0       # A(C2a), state read+write at the reference's granularity
+METRIC = "compress MB/s, method-2 (mid.cfg) 1 MB blocks, byte-exact"
+
+
+def shard_blocks(total: int, rank: int, world: int):
+    """Contiguous block range of `rank` (blocks are independent: SURVEY.md 8e)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def reduce_max_time(t: float, device: str) -> float:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return t
+    x = torch.tensor([t], dtype=torch.float64, device=device)
+    dist.all_reduce(x, op=dist.ReduceOp.MAX)
+    return float(x.item())
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
+    """Time the CPU oracle (one block per host thread) on a bounded sample of the workload."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    from tools import synth
+    po.build()
+    cores = os.cpu_count() or 1
+    data = synth.blocks("mixed", 0, cores, BLOCK)
+    blocks = [data[i * BLOCK:(i + 1) * BLOCK].tobytes() for i in range(cores)]
+
+    def comp(b):
+        return po.compress_block_level(b, LEVEL)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        arcs = list(ex.map(comp, blocks))
+    t_c = time.perf_counter() - t0
+    out = {"value": cores * BLOCK / 1e6 / t_c, "unit": "MB/s", "cores": cores, "kind": "port",
+           "sample": "%d blocks of %d B (one per host thread), mid.cfg, oracle C++ -O2" % (cores, BLOCK),
+           "seconds": t_c}
+    if decompress and t_c < seconds_budget:
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            back = list(ex.map(lambda a: po.decompress(a, cap=BLOCK + 64)[0], arcs))
+        t_d = time.perf_counter() - t0
+        assert all(b == s for b, s in zip(back, blocks))
+        out["decompress_value"] = cores * BLOCK / 1e6 / t_d
+    t0 = time.perf_counter()
+    comp(blocks[0])
+    out["single_core_value"] = BLOCK / 1e6 / (time.perf_counter() - t0)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
+    reference does not compile, so this is the oracle port; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload_config(None, args.gpus)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(decompress=False)
+    t_steps = []
+    base = None
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        base = cpu_baseline(decompress=False)
+        t_steps.append(time.perf_counter() - t0)
+        vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": cfg, "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle (C++ restatement of the reference's interpreter semantics; ZPAQSharp is not buildable)",
+    }))
+
+
+def workload_config(batch_blocks, n_gpus):
+    return {"workload": "BASELINE configs[1]: mid.cfg (Compressor.startBlock(2)), 1,044,480-byte blocks of the "
+                        "8192-block (8 GB) synthetic mixed text/binary stream",
+            "block_bytes": BLOCK, "stream_blocks": TOTAL_BLOCKS, "batch_blocks_per_gpu": batch_blocks,
+            "parallelism": "blocks x%d GPUs, no collective" % n_gpus,
+            "l2_policy": "inputs larger than L2 (batch >= 1 GB per GPU, per-block state ~106 MiB)",
+            "sha1": True}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-blocks", type=int, default=0, help="blocks per GPU per step (0 = one resident wave)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decompress", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tools import synth
+    from zpaqsharp_b200 import libzpaq as z
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    ctx = z.Context([local])
+    stream = torch.cuda.Stream(device=dev)       # the library launches on this stream; events are recorded on it
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    hdr = z.builtin_model(LEVEL)
+    state = z.device_state_bytes(hdr)
+
+    # batch = one resident wave: what fits next to the I/O buffers
+    free, total_mem = torch.cuda.mem_get_info()
+    if args.batch_blocks:
+        B = args.batch_blocks
+    else:
+        io_per_block = BLOCK * 5                      # input + slots + out (+ slack), device resident path
+        B = int((free - (3 << 30)) // (state + io_per_block))
+        B = max(1, min(B, 148 * 16, TOTAL_BLOCKS // max(world, 1)))
+    first = (rank * B) % TOTAL_BLOCKS
+
+    host_in = torch.empty(B * BLOCK, dtype=torch.uint8).pin_memory()
+    synth.fill(host_in.numpy(), "mixed", first, B, BLOCK)
+    offs = np.arange(0, (B + 1) * BLOCK, BLOCK, dtype=np.uint64)
+    out_cap = B * (BLOCK + BLOCK // 4 + 8192)
+    host_out = torch.empty(out_cap, dtype=torch.uint8).pin_memory()
+    d_in = host_in.to(dev, non_blocking=False)
+    d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        return ctx.compress_blocks_model_dev(d_in.data_ptr(), offs, hdr, d_out.data_ptr(), out_cap)
+
+    def step_host():
+        return ctx.compress_blocks_level(host_in.numpy(), offs, LEVEL, out=host_out.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        ooff = step_device()
+    st = ctx.stats()
+    resident = st.resident_blocks
+
+    # ---- timed: device-resident path ----
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    codec_ms = []
+    launches = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        ooff = step_device()
+        s = ctx.stats()
+        codec_ms.append(s.codec_kernel_ms)
+        launches += s.launches
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t_dev = reduce_max_time(e0.elapsed_time(e1) / 1e3, dev)
+    in_bytes = B * BLOCK
+    value = world * args.steps * in_bytes / 1e6 / t_dev
+    ratio = float(ooff[B]) / in_bytes
+
+    # ---- timed: end to end through the host-buffer ABI ----
+    archive, hoff = step_host()            # warm the host path (pinned buffers, staging)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        archive, hoff = step_host()
+        s = ctx.stats()
+        h2d += s.h2d_bytes
+        d2h += s.d2h_bytes
+        launches += s.launches
+    torch.cuda.synchronize()
+    t_e2e = reduce_max_time(time.perf_counter() - t0, dev)
+    e2e_value = world * args.steps * in_bytes / 1e6 / t_e2e
+
+    # ---- decompression of the same batch (device decode + host framing parse) ----
+    dec = None
+    if not args.no_decompress:
+        arc_np = archive
+        back = np.empty(in_bytes + 64, dtype=np.uint8)
+        out, o2, sha, bst = ctx.decompress_blocks(arc_np, hoff, out=back)        # warm-up + check
+        ok = bool(np.array_equal(out, host_in.numpy())) and set(sha.tolist()) == {1}
+        barrier()
+        t0 = time.perf_counter()
+        out, o2, sha, bst = ctx.decompress_blocks(arc_np, hoff, out=back)
+        torch.cuda.synchronize()
+        t_d = reduce_max_time(time.perf_counter() - t0, dev)
+        s = ctx.stats()
+        launches += s.launches
+        dec = {"e2e_value": world * in_bytes / 1e6 / t_d, "unit": "MB/s", "codec_kernel_ms": s.codec_kernel_ms,
+               "round_trip_identical": ok, "sha1_verified_blocks": int((sha == 1).sum())}
+
+    # ---- roofline of the coding kernel ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    k_ms = sum(codec_ms) / len(codec_ms)
+    achieved = ALGO_BYTES_PER_INPUT_BYTE * in_bytes / (k_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_input_byte")
+        if traffic is not None:
+            traffic = traffic * in_bytes
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_zpaq_encode_lanes", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE,
+                "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "note": "latency-bound: one dependent predict/code/update chain per warp; see DESIGN.md"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(B, world),
+            "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d // max(args.steps, 1),
+                    "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "compression_ratio": ratio, "resident_blocks_per_gpu": int(resident),
+            "state_bytes_per_block": int(st.state_bytes_per_block), "decompress": dec,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
