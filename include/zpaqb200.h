@@ -165,8 +165,17 @@ typedef struct zpq_stats {
   uint32_t launches;                           /* kernels launched */
   uint32_t resident_blocks;                    /* blocks coded concurrently */
   uint64_t state_bytes_per_block;
+  char kernel[96];                             /* which coding kernel ran: "lanes/aot2 (HCOMP compiled)", "lanes/nvrtc", ... */
 } zpq_stats;
 int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out);
+
+/* Model specialisation, the device analogue of the reference's x86 JIT (ZPAQL.assemble,
+ * ZPAQL.cs:353-1008; Predictor.assemble_p, Predictor.cs:579-1356): generate the CUDA source of the
+ * lane-resident kernels for this header and compile it with NVRTC for sm_100a.  Needs no GPU.
+ * Returns the cubin size, or a negative error with the compiler log in `log`; `source` (may be
+ * NULL) receives the generated text. */
+int64_t zpq_specialize_model(const uint8_t* hdr, uint64_t hdr_len, char* source, uint64_t source_cap, char* log,
+                             uint64_t log_cap);
 
 /* Library / build identification: "zpaqb200 <version> sm_100a". */
 const char* zpq_version(void);

@@ -1,0 +1,18 @@
+// zpq_aot.h -- registry of specialised lane-resident kernels (internal).
+#pragma once
+#include <stddef.h>
+
+namespace zpq {
+
+struct SpecKernels {
+  const void* enc = nullptr;   // __global__ function pointer (ahead of time) or cudaKernel_t (NVRTC)
+  const void* dec = nullptr;
+  const char* origin = "";     // "aot2 (HCOMP compiled)", "nvrtc", ...
+};
+
+// Ahead-of-time kernels register themselves at library load (generated files zpq_gen_aot*.cu).
+struct AotRegistrar {
+  AotRegistrar(const unsigned char* header, size_t len, const void* enc, const void* dec, const char* origin);
+};
+
+}  // namespace zpq

@@ -21,8 +21,17 @@
 #include <mutex>
 #include <thread>
 
+#include "zpq_aot.h"
 #include "zpq_device.h"
 #include "zpq_host.h"
+
+namespace zpq {
+bool find_spec_kernels(const Header& hdr, uint32_t smem_limit, SpecKernels& out, std::string* why_not);
+void spec_set_smem_limit(uint32_t bytes);
+Bytes nvrtc_compile(const std::string& src);
+std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
+                                  const std::string& dec_kernel, bool* compiled_hcomp);
+}
 
 using namespace zpq;
 
@@ -98,6 +107,7 @@ struct Device {
     CU(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, id)); sms = v;
     CU(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, id)); smem_optin = (uint32_t)v;
     CU(codec_set_smem_limit(smem_optin));
+    spec_set_smem_limit(smem_optin);
     std::unique_ptr<Tables> t(new Tables);
     build_tables(*t);
     CU(cudaMalloc(&d_tab, sizeof(Tables)));
@@ -126,7 +136,18 @@ struct Launch {
   SmemLayout sm;
   LaunchGeom geom;
   uint32_t resident;
+  SpecKernels spec;        // specialised kernels for this header, if any
+  bool has_spec = false;
+  std::string kernel;      // what will run (for zpq_stats)
 };
+
+cudaError_t launch_codec(const Launch& L, const CodecParams& p, bool decode, cudaStream_t s) {
+  if (L.has_spec) {
+    void* args[] = {const_cast<CodecParams*>(&p)};
+    return cudaLaunchKernel(decode ? L.spec.dec : L.spec.enc, dim3(L.geom.grid), dim3(L.geom.warps_per_cta * 32), args, p.sm.total, s);
+  }
+  return decode ? launch_decode(p, L.geom, s) : launch_encode(p, L.geom, s);
+}
 
 uint32_t common_smem(const Plan& pl, SmemLayout& L) {
   uint32_t o = 0;
@@ -175,6 +196,13 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
   L.sm.total = L.sm.slices + W * L.sm.slice_bytes;
   L.geom.warps_per_cta = W;
   L.geom.lanes = (L.plan->lane_ok && !force_generic()) ? 1u : 0u;
+  L.has_spec = false;
+  L.kernel = L.geom.lanes ? "lanes/generic" : "steps/generic";
+  if (L.geom.lanes) {
+    std::string why;
+    if (find_spec_kernels(hdr, d.smem_optin, L.spec, &why)) { L.has_spec = true; L.kernel = std::string("lanes/") + L.spec.origin; }
+    else L.kernel += " (" + why.substr(0, 60) + ")";
+  }
   L.geom.grid = (uint32_t)((resident + W - 1) / W);
   L.resident = (uint32_t)resident;
 }
@@ -367,7 +395,7 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   P.queue = (uint32_t*)(meta + o_queue);
   P.sm = L.sm;
   d.t_codec.start(s);
-  CU(launch_encode(P, L.geom, s));
+  CU(launch_codec(L, P, false, s));
   d.t_codec.stop(s);
   ++launches;
 
@@ -411,6 +439,7 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   d.stats.h2d_ms = d.t_h2d.ms(); d.stats.kernel_ms = d.t_kern.ms(); d.stats.d2h_ms = d.t_d2h.ms();
   d.stats.total_ms = d.t_all.ms(); d.stats.codec_kernel_ms = d.t_codec.ms();
   d.stats.launches = launches; d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
+  snprintf(d.stats.kernel, sizeof d.stats.kernel, "%s", L.kernel.c_str());
   return total;
 }
 
@@ -590,7 +619,7 @@ void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
       P.results = (BlockResult*)(meta + o_res);
       P.njobs = (uint32_t)jobs.size(); P.resident = L.resident; P.queue = (uint32_t*)(meta + o_queue); P.sm = L.sm;
       d.t_codec.start(s);
-      CU(launch_decode(P, L.geom, s));
+      CU(launch_codec(L, P, true, s));
       d.t_codec.stop(s);
       ++launches;
       std::vector<BlockResult> r(jobs.size());
@@ -598,6 +627,7 @@ void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
       CU(cudaStreamSynchronize(s));
       codec_ms += d.t_codec.ms();
       d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
+      snprintf(d.stats.kernel, sizeof d.stats.kernel, "%s", L.kernel.c_str());
       for (size_t k = 0; k < ids.size(); ++k) res[ids[k]] = r[k];
     }
     // an unhinted block that outgrew its slot gets a larger one and the batch is decoded again
@@ -896,6 +926,24 @@ int zpq_decompress_blocks(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_of
     if (!nb) return;
     decompress_all(ctx, in, in_off, nb, out, out_cap, out_off, sha1_status, block_status);
   });
+}
+
+int64_t zpq_specialize_model(const uint8_t* hdr, uint64_t hdr_len, char* source, uint64_t source_cap, char* log, uint64_t log_cap) {
+  int64_t size = -1;
+  std::string src, msg;
+  try {
+    Header h;
+    parse_header(hdr, hdr_len, h);
+    bool compiled = false;
+    src = generate_model_source(h, "Model_rt", "zpq_enc_rt", "zpq_dec_rt", &compiled);
+    Bytes cubin = nvrtc_compile(src);
+    size = (int64_t)cubin.size();
+    msg = compiled ? "HCOMP compiled" : "HCOMP interpreted";
+  } catch (const Failure& f) { msg = f.what(); size = f.code; }
+  catch (const std::exception& e) { msg = e.what(); size = ZPQ_E_CONFIG; }
+  copy_out(src, source, source_cap);
+  copy_out(msg, log, log_cap);
+  return size;
 }
 
 int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out) {

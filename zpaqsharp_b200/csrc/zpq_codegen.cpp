@@ -1,0 +1,294 @@
+// zpq_codegen.cpp -- model specialisation: turns one block header into CUDA source for the
+// lane-resident kernels.  The reference does the same thing for x86 (ZPAQL.assemble,
+// ZPAQL.cs:353-1008; Predictor.assemble_p, Predictor.cs:579-1356): translate the component list
+// and the HCOMP program once per model into straight-line native code.  Here the target is
+// sm_100a: the text produced below is compiled ahead of time for the three built-in models
+// (zpq_gen tool, run by build.py) and at run time through NVRTC for every other header.
+//
+// What gets fixed at compile time: which component types exist and on which lanes, the dependency
+// levels (one SHFL + one predicated evaluation per level instead of a run-time walk), MIX shapes
+// (weights held in registers, next rows prefetched) and the HCOMP program (ZPAQL -> C with
+// gotos, executed uniformly by all lanes).  Table offsets stay run-time (they depend on the
+// shared-memory budget of the launch) and reach the lanes' registers through lane_load().
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+
+#include "zpq_host.h"
+
+namespace zpq {
+
+namespace {
+
+const char* kReg[4] = {"a", "b", "c", "d"};
+
+std::string M_(const char* idx) { return std::string("M[(") + idx + ") & MMASK]"; }
+std::string H_(const char* idx) { return std::string("H[(") + idx + ") & HMASK]"; }
+
+// rvalue of source field sss (7 = immediate n)
+std::string src_expr(int s, int n) {
+  switch (s) {
+    case 0: case 1: case 2: case 3: return kReg[s];
+    case 4: return "(uint32_t)" + M_("b");
+    case 5: return "(uint32_t)" + M_("c");
+    case 6: return H_("d");
+    default: return std::to_string(n) + "u";
+  }
+}
+// statement assigning expression e to destination field ddd
+std::string store_stmt(int ddd, const std::string& e) {
+  switch (ddd) {
+    case 0: case 1: case 2: case 3: return std::string(kReg[ddd]) + " = " + e + ";";
+    case 4: return M_("b") + " = (uint8_t)(" + e + ");";
+    case 5: return M_("c") + " = (uint8_t)(" + e + ");";
+    default: return H_("d") + " = " + e + ";";
+  }
+}
+
+// Translate a ZPAQL program (incl. END byte) to the body of a C function.  Returns false when
+// the program cannot be compiled faithfully (jump into the middle of an instruction, undefined
+// opcode on a reachable path is still fine: it becomes `goto Lerr`).
+bool translate_zpaql(const uint8_t* code, int len, std::ostringstream& o) {
+  // linear sweep: instruction starts
+  std::vector<int> start(len + 1, 0);
+  std::vector<int> ilen(len + 1, 0);
+  for (int pc = 0; pc < len;) {
+    const int op = code[pc];
+    const int l = op == 255 ? 3 : (op & 7) == 7 ? 2 : 1;
+    if (pc + l > len) break;   // trailing partial instruction: never reached in a well formed program
+    start[pc] = 1; ilen[pc] = l;
+    pc += l;
+  }
+  std::set<int> targets;
+  for (int pc = 0; pc < len; ++pc) {
+    if (!start[pc]) continue;
+    const int op = code[pc];
+    int t = -1;
+    if (op == 39 || op == 47 || op == 63) t = pc + 2 + (((code[pc + 1] + 128) & 255) - 128);
+    else if (op == 255) t = code[pc + 1] + 256 * code[pc + 2];
+    if (t >= 0) {
+      if (t < len && !start[t]) return false;
+      targets.insert(t);
+    }
+  }
+  auto jump = [&](int from, int t) {
+    std::string g;
+    if (t < 0 || t >= len) return std::string("goto Lerr;");
+    if (t <= from) g = "if (--budget == 0) goto Lerr; ";
+    return g + "goto L" + std::to_string(t) + ";";
+  };
+  static const char* bin[14] = {"+", "-", "*", "/", "%", "&", "&~", "|", "^", "<<", ">>", "==", "<", ">"};
+  for (int pc = 0; pc < len; ++pc) {
+    if (!start[pc]) continue;
+    if (targets.count(pc)) o << "  L" << pc << ":;\n";
+    const int op = code[pc], n = ilen[pc] > 1 ? code[pc + 1] : 0;
+    o << "  ";
+    if (op < 64) {
+      const int ddd = op >> 3, x = op & 7;
+      if (ddd == 7) {
+        if (x == 0) o << "goto Lhalt;";
+        else if (x == 1) o << "/* out: no destination in HCOMP */;";
+        else if (x == 3) o << "a = (a + " << M_("b") << " + 512u) * 773u;";
+        else if (x == 4) o << H_("d") << " = (" << H_("d") << " + a + 512u) * 773u;";
+        else if (x == 7) o << jump(pc, pc + 2 + (((n + 128) & 255) - 128));
+        else o << "goto Lerr;";
+      } else if (x == 7) {
+        if (ddd < 4) o << kReg[ddd] << " = R[" << n << "];";
+        else if (ddd == 4) o << "if (f) { " << jump(pc, pc + 2 + (((n + 128) & 255) - 128)) << " }";
+        else if (ddd == 5) o << "if (!f) { " << jump(pc, pc + 2 + (((n + 128) & 255) - 128)) << " }";
+        else o << "R[" << n << "] = a;";
+      } else if (x > 4 || op == 0) o << "goto Lerr;";
+      else {
+        const std::string v = src_expr(ddd, 0);
+        if (x == 0) {  // swap with a; byte cells exchange the low 8 bits only
+          if (ddd == 0) o << ";";
+          else if (ddd == 4 || ddd == 5) o << "{ const uint32_t t = " << v << "; " << store_stmt(ddd, "a") << " a = (a & ~255u) | t; }";
+          else o << "{ const uint32_t t = " << v << "; " << store_stmt(ddd, "a") << " a = t; }";
+        } else if (x == 1) o << store_stmt(ddd, v + " + 1u");
+        else if (x == 2) o << store_stmt(ddd, v + " - 1u");
+        else if (x == 3) o << store_stmt(ddd, "~" + v);
+        else o << store_stmt(ddd, "0u");
+      }
+    } else if (op < 128) {
+      const int ddd = (op >> 3) & 7;
+      if (ddd == 7) o << "goto Lerr;";
+      else o << store_stmt(ddd, src_expr(op & 7, n));
+    } else if (op == 255) {
+      o << jump(pc, code[pc + 1] + 256 * code[pc + 2]);
+    } else {
+      const int x = (op >> 3) & 15;
+      const std::string v = src_expr(op & 7, n);
+      if (x > 13) o << "goto Lerr;";
+      else if (x == 3) o << "{ const uint32_t t = " << v << "; a = t ? a / t : 0u; }";
+      else if (x == 4) o << "{ const uint32_t t = " << v << "; a = t ? a % t : 0u; }";
+      else if (x == 6) o << "a &= ~(" << v << ");";
+      else if (x == 9) o << "a <<= ((" << v << ") & 31u);";
+      else if (x == 10) o << "a >>= ((" << v << ") & 31u);";
+      else if (x >= 11) o << "f = (a " << bin[x] << " " << v << ");";
+      else o << "a " << bin[x] << "= " << v << ";";
+    }
+    o << "\n";
+  }
+  o << "  goto Lerr;\n";  // ran off the end (the reference would execute the zero guard: error)
+  return true;
+}
+
+std::string lane_test(uint32_t mask) {
+  if (mask && !(mask & (mask - 1))) {
+    int l = 0;
+    while (!((mask >> l) & 1)) ++l;
+    return "lane == " + std::to_string(l);
+  }
+  char buf[64];
+  snprintf(buf, sizeof buf, "(0x%xu >> lane) & 1u", mask);
+  return buf;
+}
+
+}  // namespace
+
+// Source of one specialised model.  `name` becomes the model struct name; the kernels are
+// extern "C" <enc_kernel> / <dec_kernel>.
+std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
+                                  const std::string& dec_kernel, bool* compiled_hcomp) {
+  std::unique_ptr<Plan> plp(new Plan);
+  Plan& pl = *plp;
+  build_plan(hdr, false, 48 * 1024, pl);
+  if (!pl.lane_ok) throw Failure(ZPQ_E_UNSUPPORTED, "model has more than 32 components: no lane-resident specialisation");
+  std::ostringstream o;
+  o << "// Generated by zpq_codegen from block header";
+  for (size_t i = 0; i < hdr.wire.size() && i < 48; ++i) { char b[8]; snprintf(b, sizeof b, " %02x", hdr.wire[i]); o << b; }
+  o << (hdr.wire.size() > 48 ? " ...\n" : "\n");
+  o << "#include \"zpq_devcore.cuh\"\nnamespace zpq {\nstruct " << name << " {\n";
+
+  uint32_t tmask[10] = {0};
+  for (int i = 0; i < pl.n; ++i) tmask[pl.comp[i].type] |= 1u << i;
+  const bool mix_regs = pl.nmix <= kMixRegs;
+  std::vector<bool> mix_ct(pl.nmix);
+  for (int k = 0; k < pl.nmix; ++k) {
+    mix_ct[k] = mix_regs && pl.mix[k].cmask == 255 && pl.mix[k].mask >= 255;
+    if (mix_ct[k])
+      o << "  typedef MixCT<" << k << ", " << (int)pl.mix[k].lane << ", " << (int)pl.mix[k].j0 << ", " << (int)pl.mix[k].m << ", "
+        << (int)pl.mix[k].rate << "> Mix" << k << ";\n";
+  }
+
+  // ---- phase A ----
+  o << "  static __device__ __forceinline__ void phase_a(const Shared& S, const WarpCtx& W, LaneRegs& r, int lane) {\n";
+  static const struct { int t; const char* fn; } pa[] = {{C_CM, "pa_cm"}, {C_ICM, "pa_icm"}, {C_ISSE, "pa_isse"},
+                                                         {C_MATCH, "pa_match"}, {C_MIX2, "pa_mix2"}, {C_SSE, "pa_sse"}};
+  for (auto& e : pa)
+    if (tmask[e.t]) o << "    if (" << lane_test(tmask[e.t]) << ") " << e.fn << "(S, W, r);\n";
+  o << "  }\n";
+
+  // ---- levels ----
+  o << "  static __device__ __forceinline__ void levels(const Shared& S, const WarpCtx& W, LaneRegs& r, int lane) {\n";
+  for (int L = 1; L <= pl.maxlevel; ++L) {
+    uint32_t lm[10] = {0};
+    for (int i = 0; i < pl.n; ++i)
+      if (pl.comp[i].level == L && pl.comp[i].type != C_MIX) lm[pl.comp[i].type] |= 1u << i;
+    const bool any = lm[C_ISSE] || lm[C_AVG] || lm[C_MIX2] || lm[C_SSE];
+    if (any) {
+      o << "    {  // level " << L << "\n      const int pj = __shfl_sync(ZPQ_FULL, r.p, r.srcj);\n";
+      if (lm[C_AVG] || lm[C_MIX2]) o << "      const int pk = __shfl_sync(ZPQ_FULL, r.p, r.srck);\n";
+      if (lm[C_ISSE]) o << "      if (" << lane_test(lm[C_ISSE]) << ") r.p = ev_isse(r, pj);\n";
+      if (lm[C_AVG]) o << "      if (" << lane_test(lm[C_AVG]) << ") r.p = ev_avg(r, pj, pk);\n";
+      if (lm[C_MIX2]) o << "      if (" << lane_test(lm[C_MIX2]) << ") r.p = ev_mix2(r, pj, pk);\n";
+      if (lm[C_SSE]) o << "      if (" << lane_test(lm[C_SSE]) << ") r.p = ev_sse(S, r, pj);\n";
+      o << "    }\n";
+    }
+    for (int k = 0; k < pl.nmix; ++k)
+      if (pl.mix[k].level == L) {
+        if (mix_ct[k]) o << "    Mix" << k << "::predict(S.mix[" << k << "], W, r, lane);\n";
+        else o << "    mix_predict_rt(S.mix[" << k << "], W, r, lane);\n";
+      }
+  }
+  o << "  }\n";
+
+  // ---- update ----
+  o << "  static __device__ __forceinline__ void update(const Shared& S, const WarpCtx& W, LaneRegs& r, int lane, int y) {\n";
+  if (tmask[C_ISSE] || tmask[C_MIX2]) o << "    const int pj = __shfl_sync(ZPQ_FULL, r.p, r.srcj);\n";
+  if (tmask[C_MIX2]) o << "    const int pk = __shfl_sync(ZPQ_FULL, r.p, r.srck);\n";
+  if (tmask[C_CM]) o << "    if (" << lane_test(tmask[C_CM]) << ") up_cm(S, r, y);\n";
+  if (tmask[C_ICM]) o << "    if (" << lane_test(tmask[C_ICM]) << ") up_icm(S, W, r, y);\n";
+  if (tmask[C_ISSE]) o << "    if (" << lane_test(tmask[C_ISSE]) << ") up_isse(S, W, r, y, pj);\n";
+  if (tmask[C_MATCH]) o << "    if (" << lane_test(tmask[C_MATCH]) << ") up_match(r, y);\n";
+  if (tmask[C_MIX2]) o << "    if (" << lane_test(tmask[C_MIX2]) << ") up_mix2(S, r, y, pj, pk);\n";
+  if (tmask[C_SSE]) o << "    if (" << lane_test(tmask[C_SSE]) << ") up_sse(S, r, y);\n";
+  for (int k = 0; k < pl.nmix; ++k) {
+    if (mix_ct[k]) o << "    Mix" << k << "::update(S, S.mix[" << k << "], W, r, lane, y);\n";
+    else o << "    mix_update_rt(S, S.mix[" << k << "], W, r, lane, y);\n";
+  }
+  o << "  }\n";
+  o << "  static __device__ __forceinline__ void mix_shift(LaneRegs& r, int y) {\n";
+  for (int k = 0; k < pl.nmix; ++k) if (mix_ct[k]) o << "    Mix" << k << "::shift(r, y);\n";
+  o << "  }\n";
+  o << "  static __device__ __forceinline__ void mix_new_byte(const Shared& S, WarpCtx& W, LaneRegs& r, int lane) {\n";
+  for (int k = 0; k < pl.nmix; ++k)
+    if (mix_ct[k])
+      o << "    W.mixh[" << k << "] = __shfl_sync(ZPQ_FULL, r.h, " << (int)pl.mix[k].lane << "); Mix" << k << "::load_current(S.mix[" << k
+        << "], W, r, lane);\n";
+  o << "  }\n";
+
+  // ---- HCOMP ----
+  std::ostringstream body;
+  const bool ok = translate_zpaql(pl.hcomp, pl.hcomp_len, body);
+  if (compiled_hcomp) *compiled_hcomp = ok;
+  o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane) {\n";
+  if (ok) {
+    o << "    // ZPAQL -> C, run uniformly by all lanes (every lane stores the same values)\n"
+      << "    const uint32_t HMASK = " << ((1u << pl.hh) - 1) << "u, MMASK = " << (uint32_t)((1ull << pl.hm) - 1) << "u;\n"
+      << "    uint32_t* const H = env.H; uint8_t* const M = env.M; uint32_t* const R = env.R;\n"
+      << "    uint32_t a = input, b = vm.b, c = vm.c, d = vm.d, f = vm.f;\n"
+      << "    int budget = 1 << 20, rc = 0;\n"
+      << "    (void)HMASK; (void)MMASK; (void)H; (void)M; (void)R; (void)budget;\n"
+      << "    __syncwarp();\n"
+      << body.str()
+      << "  Lerr: rc = 1;\n"
+      << "  Lhalt:\n"
+      << "    vm.b = b; vm.c = c; vm.d = d; vm.f = f;\n"
+      << "    __syncwarp();\n"
+      << "    return rc;\n";
+  } else {
+    o << "    return GenericModel::hcomp(S, W, vm, env, input, lane);\n";
+  }
+  o << "  }\n};\n}  // namespace zpq\n\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << enc_kernel << "(const zpq::CodecParams P) {\n"
+    << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::encode_lanes_body<zpq::" << name << ">(P, smem);\n}\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << dec_kernel << "(const zpq::CodecParams P) {\n"
+    << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::decode_lanes_body<zpq::" << name << ">(P, smem);\n}\n";
+  return o.str();
+}
+
+}  // namespace zpq
+
+#ifdef ZPQ_GEN_MAIN
+// zpq_gen: emits the ahead-of-time specialisations of the built-in models (build.py runs it).
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: zpq_gen <outdir>\n"); return 2; }
+  try {
+    for (int level = 1; level <= 3; ++level) {
+      zpq::Bytes wire;
+      zpq::builtin_model(level, wire);
+      zpq::Header h;
+      zpq::parse_header(wire.data(), wire.size(), h);
+      const std::string id = "aot" + std::to_string(level);
+      bool compiled = false;
+      std::string src = zpq::generate_model_source(h, "Model_" + id, "zpq_enc_" + id, "zpq_dec_" + id, &compiled);
+      std::ostringstream reg;
+      reg << "\n#include \"zpq_aot.h\"\nnamespace {\nconst unsigned char kHeader[] = {";
+      for (size_t i = 0; i < wire.size(); ++i) reg << (int)wire[i] << (i + 1 < wire.size() ? "," : "");
+      reg << "};\nconst zpq::AotRegistrar kReg(kHeader, sizeof kHeader, (const void*)zpq_enc_" << id << ", (const void*)zpq_dec_" << id
+          << ", \"" << id << (compiled ? " (HCOMP compiled)" : " (HCOMP interpreted)") << "\");\n}\n";
+      const std::string path = std::string(argv[1]) + "/zpq_gen_" + id + ".cu";
+      FILE* f = fopen(path.c_str(), "w");
+      if (!f) { perror(path.c_str()); return 1; }
+      fputs(src.c_str(), f);
+      fputs(reg.str().c_str(), f);
+      fclose(f);
+    }
+  } catch (const std::exception& e) { fprintf(stderr, "zpq_gen: %s\n", e.what()); return 1; }
+  return 0;
+}
+#endif

@@ -8,37 +8,6 @@
 
 namespace zpq {
 
-// Offsets (bytes) of the CTA-common part of dynamic shared memory.
-struct SmemLayout {
-  uint32_t stretch, squash, dt, dt2k, ns, comp, order, steps, mix, hcomp;  // hcomp == kNoSmem: read from the plan
-  uint32_t slices;        // first per-block slice
-  uint32_t slice_bytes;   // == plan.smem_warp_bytes
-  uint32_t total;         // dynamic shared bytes of the launch
-};
-
-struct CodecParams {
-  const Plan* plan;
-  const Tables* tab;
-  uint8_t* arenas;            // resident_blocks * arena_stride bytes
-  uint64_t arena_stride;
-  const uint8_t* in;          // encode: (pre-processed) block bytes ; decode: archive bytes
-  const uint8_t* preamble;    // encode: PCOMP preamble bytes coded before the data
-  uint8_t* out;               // encode: slot buffer ; decode: restored bytes
-  const EncJob* ejobs;
-  const DecJob* djobs;
-  const DecSeg* segs;
-  BlockResult* results;
-  uint32_t njobs;
-  uint32_t resident;          // warps that take part
-  uint32_t* queue;            // next block index (atomic)
-  SmemLayout sm;
-};
-
-struct LaunchGeom {
-  uint32_t grid, warps_per_cta;
-  uint32_t lanes;   // 1: lane-resident kernels (n <= 32), 0: step-scheduled generic kernels
-};
-
 // Launch wrappers (all asynchronous on `s`).
 cudaError_t launch_encode(const CodecParams& p, LaunchGeom g, cudaStream_t s);
 cudaError_t launch_decode(const CodecParams& p, LaunchGeom g, cudaStream_t s);

@@ -24,184 +24,11 @@
 
 #include "../../include/zpaqb200.h"
 #include "zpq_device.h"
+#include "zpq_devcore.cuh"
 
 namespace zpq {
 
-#define FULL 0xFFFFFFFFu
-constexpr int kCtaThreads = 512;
-
-// ------------------------------------------------------------------------------------------
-// Shared-memory resident read-only state of a CTA
-// ------------------------------------------------------------------------------------------
-struct Shared {
-  const int16_t* stretch;
-  const uint16_t* squash;
-  const int32_t* dt;
-  const uint16_t* dt2k;
-  const uint8_t* ns;
-  const CompDesc* comp;
-  const uint8_t* order;
-  const Step* steps;
-  const uint8_t* hcomp;  // shared copy when it fits, else the plan's global copy
-  const MixDesc* mix;
-  int n, nsteps, hcomp_len, nmix, maxlevel;
-};
-
-// Per-block (per-warp) mutable context.
-struct Blk {
-  uint8_t* arena;
-  uint8_t* slice;
-  int32_t* p;        // stretched predictions, one per component (shared)
-  uint32_t* st;      // 5 words per component: cxt, c, a, b, limit (shared)
-  uint32_t* H; uint32_t hmask;
-  uint8_t* M; uint32_t mmask;
-  uint32_t* R;
-  int c8, hmap4;
-  uint32_t status;
-};
-
-// ZPAQL machine registers (meaningful on lane 0 only)
-struct VM {
-  uint32_t b, c, d, f;
-};
-
-struct VMEnv {
-  const uint8_t* code; int len;         // program incl. END byte; pc is relative to code
-  uint32_t* H; uint32_t hmask;
-  uint8_t* M; uint32_t mmask;
-  uint32_t* R;
-  uint8_t* out; uint64_t out_pos, out_cap;  // OUT destination (decode post-processing only)
-};
-
-__device__ __forceinline__ int clamp2k(int x) { return max(-2048, min(2047, x)); }
-__device__ __forceinline__ int clamp512k(int x) { return max(-(1 << 19), min((1 << 19) - 1, x)); }
-
-// ------------------------------------------------------------------------------------------
-// ZPAQL interpreter (ZPAQL.cs:1028-1265), decoded by instruction field.  Runs on one lane.
-// Returns 0 on HALT, 1 on an execution error, -1 when the instruction budget is spent.
-// ------------------------------------------------------------------------------------------
-__device__ __noinline__ int zpaql_run(VM& vm, VMEnv& e, uint32_t input, uint64_t budget) {
-  uint32_t a = input, b = vm.b, c = vm.c, d = vm.d, f = vm.f;
-  int pc = 0, rc = -1;
-  const uint8_t* code = e.code;
-  const int len = e.len;
-#define MB e.M[b & e.mmask]
-#define MC e.M[c & e.mmask]
-#define HD e.H[d & e.hmask]
-  while (budget--) {
-    if ((unsigned)pc >= (unsigned)len) { rc = 1; break; }
-    const int op = code[pc++];
-    if (op < 64) {
-      const int ddd = op >> 3, x = op & 7;
-      if (ddd == 7) {
-        if (x == 0) { rc = 0; break; }                                   // HALT
-        else if (x == 1) {                                               // OUT
-          if (e.out) { if (e.out_pos < e.out_cap) e.out[e.out_pos] = (uint8_t)a; ++e.out_pos; }
-        } else if (x == 3) a = (a + MB + 512) * 773;                      // HASH
-        else if (x == 4) HD = (HD + a + 512) * 773;                       // HASHD
-        else if (x == 7) pc += ((code[pc] + 128) & 255) - 127;            // JMP
-        else { rc = 1; break; }
-        continue;
-      }
-      if (x == 7) {
-        const int n = code[pc];
-        if (ddd < 4) { const uint32_t v = e.R[n]; ++pc; if (ddd == 0) a = v; else if (ddd == 1) b = v; else if (ddd == 2) c = v; else d = v; }
-        else if (ddd == 4) { if (f) pc += ((n + 128) & 255) - 127; else ++pc; }   // JT
-        else if (ddd == 5) { if (!f) pc += ((n + 128) & 255) - 127; else ++pc; }  // JF
-        else { e.R[n] = a; ++pc; }                                                 // R=A
-        continue;
-      }
-      if (x > 4 || op == 0) { rc = 1; break; }
-      uint32_t v;
-      switch (ddd) {
-        case 0: v = a; break; case 1: v = b; break; case 2: v = c; break; case 3: v = d; break;
-        case 4: v = MB; break; case 5: v = MC; break; default: v = HD; break;
-      }
-      uint32_t w;
-      if (x == 0) { w = a; a = (ddd == 4 || ddd == 5) ? ((a & ~255u) | v) : v; }  // swap (low byte only for M)
-      else if (x == 1) w = v + 1;
-      else if (x == 2) w = v - 1;
-      else if (x == 3) w = ~v;
-      else w = 0;
-      switch (ddd) {
-        case 0: if (x) a = w; break;
-        case 1: b = w; break; case 2: c = w; break; case 3: d = w; break;
-        case 4: MB = (uint8_t)w; break; case 5: MC = (uint8_t)w; break; default: HD = w; break;
-      }
-      continue;
-    }
-    if (op == 255) {                                                      // LJ
-      pc = code[pc] + 256 * code[pc + 1];
-      if (pc >= len) { rc = 1; break; }
-      continue;
-    }
-    const int s = op & 7;
-    uint32_t v;
-    switch (s) {
-      case 0: v = a; break; case 1: v = b; break; case 2: v = c; break; case 3: v = d; break;
-      case 4: v = MB; break; case 5: v = MC; break; case 6: v = HD; break;
-      default: v = code[pc++]; break;
-    }
-    if (op < 128) {                                                       // assignment
-      const int ddd = (op >> 3) & 7;
-      if (ddd == 7) { rc = 1; break; }
-      switch (ddd) {
-        case 0: a = v; break; case 1: b = v; break; case 2: c = v; break; case 3: d = v; break;
-        case 4: MB = (uint8_t)v; break; case 5: MC = (uint8_t)v; break; default: HD = v; break;
-      }
-      continue;
-    }
-    const int x = (op >> 3) & 15;
-    if (x > 13) { rc = 1; break; }
-    switch (x) {
-      case 0: a += v; break;
-      case 1: a -= v; break;
-      case 2: a *= v; break;
-      case 3: a = v ? a / v : 0; break;
-      case 4: a = v ? a % v : 0; break;
-      case 5: a &= v; break;
-      case 6: a &= ~v; break;
-      case 7: a |= v; break;
-      case 8: a ^= v; break;
-      case 9: a <<= (v & 31); break;
-      case 10: a >>= (v & 31); break;
-      case 11: f = (a == v); break;
-      case 12: f = (a < v); break;
-      default: f = (a > v); break;
-    }
-  }
-#undef MB
-#undef MC
-#undef HD
-  vm.b = b; vm.c = c; vm.d = d; vm.f = f;
-  return rc;
-}
-
-// ------------------------------------------------------------------------------------------
-// Table initialisation by the owning warp (Predictor.cs:96-165)
-// ------------------------------------------------------------------------------------------
-__device__ void init_block_state(const Plan* plan, const Tables* tab, uint8_t* arena, uint8_t* slice, int lane) {
-  const int nops = plan->ninit;
-  for (int k = 0; k < nops; ++k) {
-    const InitOp op = plan->init[k];
-    uint8_t* dst = op.to_smem ? slice + op.dst : arena + op.dst;
-    if (op.kind == 0) {
-      const uint4 v = make_uint4(op.value, op.value, op.value, op.value);
-      uint4* q = reinterpret_cast<uint4*>(dst);
-      const uint64_t n16 = op.bytes >> 4;
-      for (uint64_t i = lane; i < n16; i += 32) q[i] = v;
-    } else {
-      uint32_t* q = reinterpret_cast<uint32_t*>(dst);
-      const uint64_t nw = op.bytes >> 2;
-      if (op.kind == 1) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->icm_init[i & 255]; }
-      else if (op.kind == 2) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->isse_init[i & 511]; }
-      else {
-        const uint32_t w = tab->sse_init[lane] | op.value;  // period 32 == warp width
-        for (uint64_t i = lane; i < nw; i += 32) q[i] = w;
-      }
-    }
-  }
-}
+#define FULL ZPQ_FULL
 
 // ------------------------------------------------------------------------------------------
 // Hash-row lookup for ICM / ISSE (Predictor.cs:550-567).  Rows are 16 bytes:
@@ -295,15 +122,6 @@ __device__ __forceinline__ void predict_one(const Shared& S, Blk& w, int i) {
     default: return;
   }
   w.p[i] = pr;
-}
-
-// restored train(), Predictor.cs:1031-1036
-__device__ __forceinline__ void train(const Shared& S, uint32_t* cm, uint32_t limit, int y) {
-  uint32_t pn = *cm;
-  const uint32_t count = pn & 0x3ff;
-  const int err = y * 32767 - (int)(pn >> 17);
-  pn += ((uint32_t)err * (uint32_t)S.dt[count] & 0xFFFFFC00u) + (count < limit);
-  *cm = pn;
 }
 
 // One lane-owned component: update with coded bit y (Predictor.cs:365-459)
@@ -419,46 +237,6 @@ __device__ __forceinline__ void update_bit(const Shared& S, Blk& w, VM& vm, VMEn
   __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------
-// CTA prologue: stage tables and model descriptors into shared memory.
-// ------------------------------------------------------------------------------------------
-__device__ void stage_shared(const CodecParams& P, uint8_t* smem, Shared& S) {
-  const Plan* plan = P.plan;
-  const SmemLayout& L = P.sm;
-  {  // stretch, squash, dt, dt2k, ns are the first 79360 bytes of Tables, in this order
-    const uint4* src = reinterpret_cast<const uint4*>(P.tab);
-    uint4* dst = reinterpret_cast<uint4*>(smem + L.stretch);
-    for (int i = threadIdx.x; i < 79360 / 16; i += blockDim.x) dst[i] = src[i];
-  }
-  const int n = plan->n, ns = plan->nsteps;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(plan->comp);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + L.comp);
-    for (int i = threadIdx.x; i < n * (int)(sizeof(CompDesc) / 4); i += blockDim.x) dst[i] = src[i];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) smem[L.order + i] = plan->order[i];
-    const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(plan->steps);
-    uint32_t* sdst = reinterpret_cast<uint32_t*>(smem + L.steps);
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) sdst[i] = ssrc[i];
-    if (L.hcomp != kNoSmem)
-      for (int i = threadIdx.x; i < plan->hcomp_len + 8; i += blockDim.x) smem[L.hcomp + i] = plan->hcomp[i];
-    const uint32_t* msrc = reinterpret_cast<const uint32_t*>(plan->mix);
-    uint32_t* mdst = reinterpret_cast<uint32_t*>(smem + L.mix);
-    for (int i = threadIdx.x; i < plan->nmix * (int)(sizeof(MixDesc) / 4); i += blockDim.x) mdst[i] = msrc[i];
-  }
-  __syncthreads();
-  S.stretch = reinterpret_cast<const int16_t*>(smem + L.stretch);
-  S.squash = reinterpret_cast<const uint16_t*>(smem + L.squash);
-  S.dt = reinterpret_cast<const int32_t*>(smem + L.dt);
-  S.dt2k = reinterpret_cast<const uint16_t*>(smem + L.dt2k);
-  S.ns = smem + L.ns;
-  S.comp = reinterpret_cast<const CompDesc*>(smem + L.comp);
-  S.order = smem + L.order;
-  S.steps = reinterpret_cast<const Step*>(smem + L.steps);
-  S.hcomp = L.hcomp != kNoSmem ? smem + L.hcomp : plan->hcomp;
-  S.mix = reinterpret_cast<const MixDesc*>(smem + L.mix);
-  S.n = n; S.nsteps = ns; S.hcomp_len = plan->hcomp_len; S.nmix = plan->nmix; S.maxlevel = plan->maxlevel;
-}
-
 // Reset everything a new block needs (Predictor.init + ZPAQL.inith).
 __device__ void begin_block(const CodecParams& P, const Shared& S, Blk& w, VM& vm, VMEnv& env, int lane) {
   const Plan* plan = P.plan;
@@ -477,20 +255,6 @@ __device__ void begin_block(const CodecParams& P, const Shared& S, Blk& w, VM& v
   env.H = w.H; env.hmask = w.hmask; env.M = w.M; env.mmask = w.mmask; env.R = w.R;
   env.out = nullptr; env.out_pos = 0; env.out_cap = 0;
   __syncwarp();
-}
-
-__device__ __forceinline__ void bind_block(const CodecParams& P, uint8_t* smem, Blk& w, uint32_t gw, int warp) {
-  const Plan* plan = P.plan;
-  w.arena = P.arenas + (uint64_t)gw * P.arena_stride;
-  w.slice = smem + P.sm.slices + (uint32_t)warp * P.sm.slice_bytes;
-  w.p = reinterpret_cast<int32_t*>(w.slice + plan->smem_p);
-  w.st = reinterpret_cast<uint32_t*>(w.slice + plan->smem_st);
-  w.H = plan->smem_h != kNoSmem ? reinterpret_cast<uint32_t*>(w.slice + plan->smem_h)
-                                : reinterpret_cast<uint32_t*>(w.arena + plan->off_h);
-  w.hmask = (1u << plan->hh) - 1;
-  w.M = w.arena + plan->off_m;
-  w.mmask = (uint32_t)((1ull << plan->hm) - 1);
-  w.R = reinterpret_cast<uint32_t*>(w.arena + plan->off_r);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -874,9 +638,17 @@ cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const uin
 
 }  // namespace zpq
 
-#include "zpq_lane.cuh"
-
 namespace zpq {
+
+// Lane-resident kernels with the run-time model walker (any model with 1..32 components).
+__global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_encode_lanes(const CodecParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  encode_lanes_body<GenericModel>(P, smem);
+}
+__global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode_lanes(const CodecParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  decode_lanes_body<GenericModel>(P, smem);
+}
 
 cudaError_t codec_set_smem_limit(uint32_t bytes) {
   const void* ks[4] = {(const void*)k_zpaq_encode, (const void*)k_zpaq_decode, (const void*)k_zpaq_encode_lanes,

@@ -161,7 +161,9 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   const uint64_t hbytes = 4ull << h.hh;
   if (h.n > 0 && hbytes <= 2048 && slice + hbytes <= smem_budget) { pl.smem_h = stake((uint32_t)hbytes); fill(pl.smem_h, hbytes, 0, 0, true); }
   else { pl.smem_h = kNoSmem; pl.off_h = take(hbytes); fill(pl.off_h, hbytes, 0, 0, false); }
-  pl.off_m = take(1ull << h.hm); fill(pl.off_m, 1ull << h.hm, 0, 0, false);
+  const uint64_t mbytes = 1ull << h.hm;
+  if (h.n > 0 && mbytes <= 1024 && slice + mbytes <= smem_budget) { pl.smem_m = stake((uint32_t)std::max<uint64_t>(mbytes, 16)); fill(pl.smem_m, mbytes, 0, 0, true); }
+  else { pl.smem_m = kNoSmem; pl.off_m = take(mbytes); fill(pl.off_m, mbytes, 0, 0, false); }
   pl.off_r = take(1024); fill(pl.off_r, 1024, 0, 0, false);
   pl.smem_cm = slice;
 

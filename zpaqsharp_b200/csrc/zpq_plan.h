@@ -6,7 +6,12 @@
 // by dependency level so that one warp evaluates a level across its lanes), the table
 // initialisation list and the HCOMP bytecode.
 #pragma once
+#ifdef __CUDACC_RTC__
+typedef unsigned char uint8_t; typedef signed char int8_t; typedef unsigned short uint16_t; typedef short int16_t;
+typedef unsigned int uint32_t; typedef int int32_t; typedef unsigned long long uint64_t; typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 
 namespace zpq {
 
@@ -59,6 +64,7 @@ struct MixDesc {
   uint64_t tab;        // arena offset of the weight rows
 };
 constexpr int kMaxMix = 16;
+constexpr int kMixRegs = 4;   // MIX components whose weights a specialised kernel keeps in registers
 
 struct Plan {
   int32_t n;                    // components
@@ -73,6 +79,7 @@ struct Plan {
   int32_t lane_ok;              // 1: n <= 32 and few MIXes -> lane-resident kernel applies
   int32_t nmix, maxlevel;
   uint32_t smem_rows;           // slice offset of the 32 x 16-byte hash-row cache
+  uint32_t smem_m;              // slice offset of the HCOMP M array when it is small, else kNoSmem
   MixDesc mix[kMaxMix];
   CompDesc comp[kMaxComp];
   uint8_t order[kMaxComp];      // components sorted by (level, coop)
@@ -116,6 +123,37 @@ struct Tables {
   uint32_t icm_init[256];   // cminit(j)                       Predictor.cs:111-112
   uint32_t isse_init[512];  // {1<<15, clamp512k(stretch(cminit(j)>>8)*1024)}  Predictor.cs:150-155
   uint32_t sse_init[32];    // squash((j&31)*64-992)<<17       Predictor.cs:163-164
+};
+
+// Offsets (bytes) of the CTA-common part of dynamic shared memory.
+struct SmemLayout {
+  uint32_t stretch, squash, dt, dt2k, ns, comp, order, steps, mix, hcomp;  // hcomp == kNoSmem: read from the plan
+  uint32_t slices;        // first per-block slice
+  uint32_t slice_bytes;   // == plan.smem_warp_bytes
+  uint32_t total;         // dynamic shared bytes of the launch
+};
+
+struct CodecParams {
+  const Plan* plan;
+  const Tables* tab;
+  uint8_t* arenas;            // resident_blocks * arena_stride bytes
+  uint64_t arena_stride;
+  const uint8_t* in;          // encode: (pre-processed) block bytes ; decode: archive bytes
+  const uint8_t* preamble;    // encode: PCOMP preamble bytes coded before the data
+  uint8_t* out;               // encode: slot buffer ; decode: restored bytes
+  const EncJob* ejobs;
+  const DecJob* djobs;
+  const DecSeg* segs;
+  BlockResult* results;
+  uint32_t njobs;
+  uint32_t resident;          // warps that take part
+  uint32_t* queue;            // next block index (atomic)
+  SmemLayout sm;
+};
+
+struct LaunchGeom {
+  uint32_t grid, warps_per_cta;
+  uint32_t lanes;   // 1: lane-resident kernels (n <= 32), 0: step-scheduled generic kernels
 };
 
 }  // namespace zpq

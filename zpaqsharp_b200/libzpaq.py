@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "zpq_make_config", "zpq_expand_method", "zpq_compile_config", "zpq_builtin_model", "zpq_block_memory",
     "zpq_device_state_bytes", "zpq_compress_blocks", "zpq_compress_blocks_level", "zpq_compress_blocks_model",
     "zpq_compress_blocks_model_dev", "zpq_find_blocks", "zpq_decompress_blocks", "zpq_decompressed_bound",
-    "zpq_get_stats", "zpq_version",
+    "zpq_get_stats", "zpq_version", "zpq_specialize_model",
 ]
 
 
@@ -42,7 +42,8 @@ class ZpaqError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
                 ("codec_kernel_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("launches", C.c_uint32), ("resident_blocks", C.c_uint32), ("state_bytes_per_block", C.c_uint64)]
+                ("launches", C.c_uint32), ("resident_blocks", C.c_uint32), ("state_bytes_per_block", C.c_uint64),
+                ("kernel", C.c_char * 96)]
 
 
 _lib = None
@@ -91,6 +92,8 @@ def load():
     L.zpq_decompressed_bound.restype = C.c_int64
     L.zpq_decompressed_bound.argtypes = [u8p, u64p, C.c_uint32]
     L.zpq_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.zpq_specialize_model.restype = C.c_int64
+    L.zpq_specialize_model.argtypes = [u8p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
     _lib = L
     return L
 
@@ -163,6 +166,15 @@ def block_memory(hdr: bytes) -> float:
 
 def device_state_bytes(hdr: bytes, for_decode: bool = False) -> int:
     return load().zpq_device_state_bytes(hdr, len(hdr), 1 if for_decode else 0)
+
+
+def specialize_model(hdr: bytes):
+    """Generate + NVRTC-compile the specialised kernels of a header -> (cubin size or error, source, log)."""
+    L = load()
+    src = C.create_string_buffer(1 << 20)
+    log = C.create_string_buffer(1 << 16)
+    n = L.zpq_specialize_model(hdr, len(hdr), src, 1 << 20, log, 1 << 16)
+    return n, src.value.decode(), log.value.decode(errors="replace")
 
 
 def find_blocks(archive) -> list:
