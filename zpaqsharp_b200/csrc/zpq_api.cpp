@@ -180,7 +180,7 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
     uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
     if ((uint64_t)W * L.plan->smem_warp_bytes <= avail) break;
     uint32_t budget = avail / W;
-    uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64 + 512, 128);
+    uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64 + 512 + 256, 128);
     if (budget >= minimal) {
       build_plan(hdr, decode, budget & ~127u, *L.plan);
       common = common_smem(*L.plan, L.sm);

@@ -171,20 +171,69 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
     mix_ct[k] = mix_regs && pl.mix[k].cmask == 255 && pl.mix[k].mask >= 255;
     if (mix_ct[k])
       o << "  typedef MixCT<" << k << ", " << (int)pl.mix[k].lane << ", " << (int)pl.mix[k].j0 << ", " << (int)pl.mix[k].m << ", "
-        << (int)pl.mix[k].rate << "> Mix" << k << ";\n";
+        << (int)pl.mix[k].rate << ", " << pl.mix[k].mask << "u> Mix" << k << ";\n";
   }
 
   // ---- phase A ----
   o << "  static __device__ __forceinline__ void phase_a(const Shared& S, const WarpCtx& W, LaneRegs& r, int lane) {\n";
   static const struct { int t; const char* fn; } pa[] = {{C_CM, "pa_cm"}, {C_ICM, "pa_icm"}, {C_ISSE, "pa_isse"},
                                                          {C_MATCH, "pa_match"}, {C_MIX2, "pa_mix2"}, {C_SSE, "pa_sse"}};
+  const uint32_t umask = tmask[C_ICM] | tmask[C_ISSE] | tmask[C_MATCH];
+  if (umask) o << "    pa_unified(S, W, r);   // ICM + ISSE + MATCH, branch-free on all lanes\n";
   for (auto& e : pa)
-    if (tmask[e.t]) o << "    if (" << lane_test(tmask[e.t]) << ") " << e.fn << "(S, W, r);\n";
+    if (tmask[e.t] && e.t != C_ICM && e.t != C_ISSE && e.t != C_MATCH) o << "    if (" << lane_test(tmask[e.t]) << ") " << e.fn << "(S, W, r);\n";
+  if (tmask[C_ISSE]) o << "    __syncwarp();   // ISSE chain slots are read by every lane\n";
   o << "  }\n";
 
   // ---- levels ----
   o << "  static __device__ __forceinline__ void levels(const Shared& S, const WarpCtx& W, LaneRegs& r, int lane) {\n";
-  for (int L = 1; L <= pl.maxlevel; ++L) {
+  // An ISSE chain (every level holds one ISSE fed by the component of the level before, the usual
+  // shape of ICM-ISSE-ISSE... models) is evaluated redundantly by all lanes from the {w0, w1*64}
+  // slots the owners published in phase A: no SHFL and no branch per level.
+  auto sole_isse = [&](int L) {   // lane of the only non-MIX component at level L if it is an ISSE, else -1
+    int found = -1, count = 0;
+    for (int i = 0; i < pl.n; ++i)
+      if (pl.comp[i].level == L && pl.comp[i].type != C_MIX && pl.comp[i].type != C_CONS) { found = i; ++count; }
+    return (count == 1 && pl.comp[found].type == C_ISSE) ? found : -1;
+  };
+  auto mixes_at = [&](int L) {
+    for (int k = 0; k < pl.nmix; ++k)
+      if (pl.mix[k].level == L) {
+        if (mix_ct[k]) o << "    Mix" << k << "::predict(W, r, lane);\n";
+        else o << "    mix_predict_rt(S.mix[" << k << "], W, r, lane);\n";
+      }
+  };
+  bool any_chain = false; (void)any_chain;
+  for (int L = 1; L <= pl.maxlevel;) {
+    // try to start a chain at level L
+    std::vector<int> chain;
+    int lane0 = sole_isse(L);
+    if (lane0 >= 0) {
+      chain.push_back(lane0);
+      int LL = L + 1;
+      while (LL <= pl.maxlevel) {
+        bool mix_between = false;
+        for (int k = 0; k < pl.nmix; ++k) if (pl.mix[k].level == LL - 1) mix_between = true;
+        int nx = sole_isse(LL);
+        if (mix_between || nx < 0 || pl.comp[nx].a[1] != chain.back()) break;
+        chain.push_back(nx);
+        ++LL;
+      }
+    }
+    if (chain.size() >= 2) {
+      any_chain = true;
+      const int root = pl.comp[chain[0]].a[1];
+      o << "    {  // ISSE chain, levels " << L << ".." << (L + (int)chain.size() - 1) << "\n";
+      o << "      const int2* cs = r.chain - lane;\n";
+      for (size_t q = 0; q < chain.size(); ++q) o << "      const int2 w" << q << " = cs[" << chain[q] << "];\n";
+      o << "      int v = __shfl_sync(ZPQ_FULL, r.p, " << root << ");\n";
+      for (size_t q = 0; q < chain.size(); ++q)
+        o << "      v = clamp2k((w" << q << ".x * v + w" << q << ".y) >> 16); r.p = lane == " << chain[q] << " ? v : r.p;\n";
+      o << "    }\n";
+      L += (int)chain.size();
+      mixes_at(L - 1);
+      continue;
+    }
     uint32_t lm[10] = {0};
     for (int i = 0; i < pl.n; ++i)
       if (pl.comp[i].level == L && pl.comp[i].type != C_MIX) lm[pl.comp[i].type] |= 1u << i;
@@ -198,11 +247,8 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
       if (lm[C_SSE]) o << "      if (" << lane_test(lm[C_SSE]) << ") r.p = ev_sse(S, r, pj);\n";
       o << "    }\n";
     }
-    for (int k = 0; k < pl.nmix; ++k)
-      if (pl.mix[k].level == L) {
-        if (mix_ct[k]) o << "    Mix" << k << "::predict(S.mix[" << k << "], W, r, lane);\n";
-        else o << "    mix_predict_rt(S.mix[" << k << "], W, r, lane);\n";
-      }
+    mixes_at(L);
+    ++L;
   }
   o << "  }\n";
 
@@ -211,13 +257,11 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   if (tmask[C_ISSE] || tmask[C_MIX2]) o << "    const int pj = __shfl_sync(ZPQ_FULL, r.p, r.srcj);\n";
   if (tmask[C_MIX2]) o << "    const int pk = __shfl_sync(ZPQ_FULL, r.p, r.srck);\n";
   if (tmask[C_CM]) o << "    if (" << lane_test(tmask[C_CM]) << ") up_cm(S, r, y);\n";
-  if (tmask[C_ICM]) o << "    if (" << lane_test(tmask[C_ICM]) << ") up_icm(S, W, r, y);\n";
-  if (tmask[C_ISSE]) o << "    if (" << lane_test(tmask[C_ISSE]) << ") up_isse(S, W, r, y, pj);\n";
-  if (tmask[C_MATCH]) o << "    if (" << lane_test(tmask[C_MATCH]) << ") up_match(r, y);\n";
+  if (tmask[C_ICM] | tmask[C_ISSE] | tmask[C_MATCH]) o << "    up_unified(S, W, r, y, " << ((tmask[C_ISSE] || tmask[C_MIX2]) ? "pj" : "0") << ");\n";
   if (tmask[C_MIX2]) o << "    if (" << lane_test(tmask[C_MIX2]) << ") up_mix2(S, r, y, pj, pk);\n";
   if (tmask[C_SSE]) o << "    if (" << lane_test(tmask[C_SSE]) << ") up_sse(S, r, y);\n";
   for (int k = 0; k < pl.nmix; ++k) {
-    if (mix_ct[k]) o << "    Mix" << k << "::update(S, S.mix[" << k << "], W, r, lane, y);\n";
+    if (mix_ct[k]) o << "    Mix" << k << "::update(S, W, r, lane, y);\n";
     else o << "    mix_update_rt(S, S.mix[" << k << "], W, r, lane, y);\n";
   }
   o << "  }\n";
@@ -227,8 +271,7 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   o << "  static __device__ __forceinline__ void mix_new_byte(const Shared& S, WarpCtx& W, LaneRegs& r, int lane) {\n";
   for (int k = 0; k < pl.nmix; ++k)
     if (mix_ct[k])
-      o << "    W.mixh[" << k << "] = __shfl_sync(ZPQ_FULL, r.h, " << (int)pl.mix[k].lane << "); Mix" << k << "::load_current(S.mix[" << k
-        << "], W, r, lane);\n";
+      o << "    W.mixh[" << k << "] = __shfl_sync(ZPQ_FULL, r.h, " << (int)pl.mix[k].lane << "); Mix" << k << "::load_current(W, r, lane);\n";
   o << "  }\n";
 
   // ---- HCOMP ----

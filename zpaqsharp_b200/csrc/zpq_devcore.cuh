@@ -193,7 +193,7 @@ __device__ __forceinline__ void init_block_state(const Plan* plan, const Tables*
     } else {
       uint32_t* q = reinterpret_cast<uint32_t*>(dst);
       const uint64_t nw = op.bytes >> 2;
-      if (op.kind == 1) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->icm_init[i & 255]; }
+      if (op.kind == 1) { for (uint64_t i = lane; i < nw; i += 32) q[i] = (i & 1) ? 0u : tab->icm_init[(i >> 1) & 255]; }
       else if (op.kind == 2) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->isse_init[i & 511]; }
       else {
         const uint32_t w = tab->sse_init[lane] | op.value;  // period 32 == warp width
@@ -279,8 +279,14 @@ struct LaneRegs {
   uint8_t* row;       // this lane's 16-byte row cache in shared memory
   // dynamic
   uint32_t cxt, c, ma, mb, mpos, h;
+  uint32_t mbyte;     // MATCH: the byte the match predicts next
+  uint32_t mbit;      // MATCH: bits of the current byte already coded
   int p, t0, t1;
-  int mw[kMixRegs], mn0[kMixRegs], mn1[kMixRegs];   // MIX k: weight `lane` of the current row / of both next rows
+  int2* chain;        // this lane's slot {w0, w1*64} for ISSE chains evaluated by the whole warp
+  // MIX k held in registers: weight `lane` of the current row and of both possible next rows
+  int mw[kMixRegs], mn0[kMixRegs], mn1[kMixRegs];
+  uint32_t moff[kMixRegs], mo0[kMixRegs], mo1[kMixRegs];   // byte offsets of those weights in the table
+  const uint8_t* mixtab[kMixRegs];
 };
 
 struct WarpCtx {
@@ -293,15 +299,19 @@ struct WarpCtx {
 __device__ __forceinline__ void lane_load(const Shared& S, const CodecParams& P, const Blk& w, LaneRegs& r, int lane) {
   r.type = C_NONE; r.level = 0; r.srcj = r.srck = 0;
   r.a1 = r.a2 = r.a3 = r.a4 = r.a5 = 0; r.mask = r.mask2 = 0;
-  r.tab = r.tab2 = nullptr; r.cm = nullptr;
+  r.tab = r.tab2 = nullptr;
+  r.cm = reinterpret_cast<uint32_t*>(const_cast<int16_t*>(S.stretch));   // readable dummy for lanes without a map
   r.row = w.slice + P.plan->smem_rows + lane * 16;
+  r.chain = reinterpret_cast<int2*>(w.slice + P.plan->smem_chain) + lane;
+  for (int k = 0; k < kMixRegs; ++k) r.mixtab[k] = k < S.nmix ? w.arena + S.mix[k].tab : w.arena;
   if (lane < S.n) {
     const CompDesc& d = S.comp[lane];
     r.type = d.type; r.level = d.level;
     r.a1 = d.a[0]; r.a2 = d.a[1]; r.a3 = d.a[2]; r.a4 = d.a[3]; r.a5 = d.a[4];
     r.mask = d.mask; r.mask2 = d.mask2;
     r.tab = w.arena + d.tab; r.tab2 = w.arena + d.tab2;
-    r.cm = d.smem_cm != kNoSmem ? reinterpret_cast<uint32_t*>(w.slice + d.smem_cm) : reinterpret_cast<uint32_t*>(w.arena + d.tab2);
+    if (d.type == C_ICM || d.type == C_ISSE)
+      r.cm = d.smem_cm != kNoSmem ? reinterpret_cast<uint32_t*>(w.slice + d.smem_cm) : reinterpret_cast<uint32_t*>(w.arena + d.tab2);
     switch (d.type) {
       case C_ISSE: case C_SSE: r.srcj = d.a[1]; break;
       case C_AVG: r.srcj = d.a[0]; r.srck = d.a[1]; break;
@@ -340,17 +350,19 @@ __device__ __forceinline__ void pa_cm(const Shared& S, const WarpCtx& W, LaneReg
 }
 __device__ __forceinline__ void pa_icm(const Shared& S, const WarpCtx& W, LaneRegs& r) {
   r.cxt = r.row[W.hmap4 & 15];
-  r.p = S.stretch[r.cm[r.cxt] >> 8];
+  r.t0 = (int)r.cm[r.cxt * 2];          // ICM maps use the 8-byte stride of ISSE maps (second word unused)
+  r.p = S.stretch[(uint32_t)r.t0 >> 8];
 }
 __device__ __forceinline__ void pa_isse(const Shared& S, const WarpCtx& W, LaneRegs& r) {
   r.cxt = r.row[W.hmap4 & 15];
   const int2 wt = *reinterpret_cast<const int2*>(r.cm + r.cxt * 2);
   r.t0 = wt.x; r.t1 = wt.y;
+  *r.chain = make_int2(wt.x, wt.y << 6);
 }
 __device__ __forceinline__ void pa_match(const Shared& S, const WarpCtx& W, LaneRegs& r) {
   if (r.ma == 0) r.p = 0;
   else {
-    const uint32_t bit = (r.tab2[(r.mpos - r.mb) & r.mask2] >> (7 - r.cxt)) & 1;
+    const uint32_t bit = (r.mbyte >> (7 - r.mbit)) & 1;
     r.c = bit;
     r.p = S.stretch[(S.dt2k[r.ma] * (1 - 2 * (int)bit)) & 32767];
   }
@@ -384,8 +396,8 @@ __device__ __forceinline__ void up_cm(const Shared& S, LaneRegs& r, int y) {
 }
 __device__ __forceinline__ void up_icm(const Shared& S, const WarpCtx& W, LaneRegs& r, int y) {
   r.row[W.hmap4 & 15] = S.ns[r.cxt * 4 + y];
-  const uint32_t pn = r.cm[r.cxt];
-  r.cm[r.cxt] = pn + (uint32_t)(((int)(y * 32767 - (pn >> 8))) >> 2);
+  const uint32_t pn = (uint32_t)r.t0;
+  r.cm[r.cxt * 2] = pn + (uint32_t)(((int)(y * 32767 - (pn >> 8))) >> 2);
 }
 __device__ __forceinline__ void up_isse(const Shared& S, const WarpCtx& W, LaneRegs& r, int y, int pj) {
   const int err = y * 32767 - (int)S.squash[r.p + 2048];
@@ -395,12 +407,18 @@ __device__ __forceinline__ void up_isse(const Shared& S, const WarpCtx& W, LaneR
   *reinterpret_cast<int2*>(r.cm + r.cxt * 2) = wt;
   r.row[W.hmap4 & 15] = S.ns[r.cxt * 4 + y];
 }
-__device__ __forceinline__ void up_match(LaneRegs& r, int y) {
-  uint8_t* buf = r.tab2;
+__device__ __forceinline__ void match_byte(const WarpCtx& W, LaneRegs& r, int y);
+// The history buffer is written once per byte (position `limit` is never read before its byte is
+// complete: offsets are non-zero modulo the buffer size), and the predicted byte is read once.
+__device__ __forceinline__ void up_match(const WarpCtx& W, LaneRegs& r, int y) {
   if ((int)r.c != y) r.ma = 0;
-  buf[r.mpos] = (uint8_t)(buf[r.mpos] * 2 + y);
-  if (++r.cxt == 8) {
-    r.cxt = 0;
+  if (++r.mbit == 8) match_byte(W, r, y);
+}
+__device__ __forceinline__ void match_byte(const WarpCtx& W, LaneRegs& r, int y) {
+  {
+    uint8_t* buf = r.tab2;
+    buf[r.mpos] = (uint8_t)(W.c8 * 2 + y);
+    r.mbit = 0;
     r.mpos = (r.mpos + 1) & r.mask2;
     uint32_t* idx = reinterpret_cast<uint32_t*>(r.tab) + (r.h & r.mask);
     if (r.ma == 0) {
@@ -409,6 +427,7 @@ __device__ __forceinline__ void up_match(LaneRegs& r, int y) {
         while (r.ma < 255 && buf[(r.mpos - r.ma - 1) & r.mask2] == buf[(r.mpos - r.ma - r.mb - 1) & r.mask2]) ++r.ma;
     } else r.ma += r.ma < 255;
     *idx = r.mpos;
+    if (r.ma) r.mbyte = buf[(r.mpos - r.mb) & r.mask2];
   }
 }
 __device__ __forceinline__ void up_mix2(const Shared& S, LaneRegs& r, int y, int pj, int pk) {
@@ -419,6 +438,40 @@ __device__ __forceinline__ void up_mix2(const Shared& S, LaneRegs& r, int y, int
 }
 __device__ __forceinline__ void up_sse(const Shared& S, LaneRegs& r, int y) {
   train(S, reinterpret_cast<uint32_t*>(r.tab) + r.cxt, r.a4 * 4u, y);
+}
+
+// ---- branch-free ICM + ISSE + MATCH (the shape of min/mid/max and most makeConfig models) -------
+// Every lane executes the same straight-line code on its own registers; lanes of other types read
+// harmless dummies and keep their state through selects, so the three per-type dependency chains
+// (row byte -> map -> stretch; dt2k -> stretch) overlap instead of running one branch after another.
+__device__ __forceinline__ void pa_unified(const Shared& S, const WarpCtx& W, LaneRegs& r) {
+  const bool icm = r.type == C_ICM, isse = r.type == C_ISSE, mat = r.type == C_MATCH;
+  const uint32_t bh = r.row[W.hmap4 & 15];
+  const int2 wt = *reinterpret_cast<const int2*>(r.cm + bh * 2);
+  const uint32_t bit = (r.mbyte >> (7 - r.mbit)) & 1;
+  const int sp = S.stretch[((uint32_t)wt.x >> 8) & 32767];
+  const int pm = S.stretch[(S.dt2k[r.ma] * (1 - 2 * (int)bit)) & 32767];
+  if (icm || isse) { r.cxt = bh; r.t0 = wt.x; r.t1 = wt.y; }
+  *r.chain = make_int2(wt.x, wt.y << 6);
+  r.p = icm ? sp : r.p;
+  if (mat) { r.c = r.ma ? bit : r.c; r.p = r.ma ? pm : 0; }
+}
+__device__ __forceinline__ void up_unified(const Shared& S, const WarpCtx& W, LaneRegs& r, int y, int pj) {
+  const bool icm = r.type == C_ICM, isse = r.type == C_ISSE;
+  const int err = y * 32767 - (int)S.squash[r.p + 2048];
+  const uint32_t nxt = S.ns[(r.cxt & 255) * 4 + y];
+  const uint32_t pn = (uint32_t)r.t0;
+  int2 wt;
+  wt.x = isse ? clamp512k(r.t0 + ((err * pj + (1 << 12)) >> 13)) : (int)(pn + (uint32_t)(((int)(y * 32767 - (pn >> 8))) >> 2));
+  wt.y = clamp512k(r.t1 + ((err + 16) >> 5));
+  if (icm || isse) {
+    *reinterpret_cast<int2*>(r.cm + r.cxt * 2) = wt;
+    r.row[W.hmap4 & 15] = (uint8_t)nxt;
+  }
+  if (r.type == C_MATCH) {
+    if ((int)r.c != y) r.ma = 0;
+    if (++r.mbit == 8) match_byte(W, r, y);
+  }
 }
 
 // ---- MIX, evaluated by the whole warp (Predictor.cs:302-316, 427-439) --------------------------
@@ -447,34 +500,42 @@ __device__ __forceinline__ void mix_update_rt(const Shared& S, const MixDesc& md
 // `lane` of the row of the current partial byte; while the bit is being coded both possible next
 // rows are fetched into r.mn0/mn1[K], so the row walk never waits for HBM inside a byte.
 // Requires cmask == 255 and at least 256 contexts (rows of c8, 2*c8 and 2*c8+1 are then distinct).
-template <int K, int MIXLANE, int J0, int M, int RATE>
+template <int K, int MIXLANE, int J0, int M, int RATE, unsigned MASK>
 struct MixCT {
-  static __device__ __forceinline__ const int* rowptr(const WarpCtx& W, const MixDesc& md, uint32_t c8) {
-    return reinterpret_cast<const int*>(W.arena + md.tab) + ((W.mixh[K] + c8) & md.mask) * M;
+  static __device__ __forceinline__ uint32_t off(const WarpCtx& W, uint32_t c8, int lane) {
+    return ((W.mixh[K] + c8) & MASK) * (uint32_t)(M * 4) + (uint32_t)lane * 4u;
   }
-  static __device__ __forceinline__ void load_current(const MixDesc& md, const WarpCtx& W, LaneRegs& r, int lane) {
-    r.mw[K] = lane < M ? rowptr(W, md, (uint32_t)W.c8)[lane] : 0;
+  static __device__ __forceinline__ void load_current(const WarpCtx& W, LaneRegs& r, int lane) {
+    r.moff[K] = off(W, (uint32_t)W.c8, lane);
+    r.mw[K] = lane < M ? *reinterpret_cast<const int*>(r.mixtab[K] + r.moff[K]) : 0;
   }
-  static __device__ __forceinline__ void predict(const MixDesc& md, const WarpCtx& W, LaneRegs& r, int lane) {
-    if (W.c8 < 128 && lane < M) {
-      r.mn0[K] = rowptr(W, md, (uint32_t)W.c8 * 2)[lane];
-      r.mn1[K] = rowptr(W, md, (uint32_t)W.c8 * 2 + 1)[lane];
+  static __device__ __forceinline__ void predict(const WarpCtx& W, LaneRegs& r, int lane) {
+    if (W.c8 < 128) {
+      r.mo0[K] = off(W, (uint32_t)W.c8 * 2, lane);
+      r.mo1[K] = off(W, (uint32_t)W.c8 * 2 + 1, lane);
+      if (lane < M) {
+        r.mn0[K] = *reinterpret_cast<const int*>(r.mixtab[K] + r.mo0[K]);
+        r.mn1[K] = *reinterpret_cast<const int*>(r.mixtab[K] + r.mo1[K]);
+      }
     }
     const int pin = __shfl_sync(ZPQ_FULL, r.p, J0 + lane);
     const int acc = __reduce_add_sync(ZPQ_FULL, (r.mw[K] >> 8) * pin);
-    if (lane == MIXLANE) r.p = clamp2k(acc >> 8);
+    r.p = lane == MIXLANE ? clamp2k(acc >> 8) : r.p;
   }
-  static __device__ __forceinline__ void update(const Shared& S, const MixDesc& md, const WarpCtx& W, LaneRegs& r, int lane, int y) {
+  static __device__ __forceinline__ void update(const Shared& S, const WarpCtx& W, LaneRegs& r, int lane, int y) {
     const int pm = __shfl_sync(ZPQ_FULL, r.p, MIXLANE);
     const int pin = __shfl_sync(ZPQ_FULL, r.p, J0 + lane);
     const int err = ((y * 32767 - (int)S.squash[pm + 2048]) * RATE) >> 4;
     if (lane < M) {
       const int w = clamp512k(r.mw[K] + ((err * pin + (1 << 12)) >> 13));
-      const_cast<int*>(rowptr(W, md, (uint32_t)W.c8))[lane] = w;
+      *reinterpret_cast<int*>(const_cast<uint8_t*>(r.mixtab[K]) + r.moff[K]) = w;
     }
   }
   // after the bit is known and before c8 changes
-  static __device__ __forceinline__ void shift(LaneRegs& r, int y) { r.mw[K] = y ? r.mn1[K] : r.mn0[K]; }
+  static __device__ __forceinline__ void shift(LaneRegs& r, int y) {
+    r.mw[K] = y ? r.mn1[K] : r.mn0[K];
+    r.moff[K] = y ? r.mo1[K] : r.mo0[K];
+  }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -518,7 +579,7 @@ struct GenericModel {
       case C_CM: up_cm(S, r, y); break;
       case C_ICM: up_icm(S, W, r, y); break;
       case C_ISSE: up_isse(S, W, r, y, pj); break;
-      case C_MATCH: up_match(r, y); break;
+      case C_MATCH: up_match(W, r, y); break;
       case C_MIX2: up_mix2(S, r, y, pj, pk); break;
       case C_SSE: up_sse(S, r, y); break;
       default: break;
@@ -538,6 +599,8 @@ struct GenericModel {
     return rc;
   }
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Probability (0..32767) that the next bit is 1.
 template <class Model>
@@ -562,6 +625,7 @@ __device__ __forceinline__ uint32_t lane_advance(const Shared& S, WarpCtx& W, La
     W.c8 = 1;
     Model::mix_new_byte(S, W, r, lane);
     if (hashed) lane_find(r, r.h + 16);
+    if (r.type == C_MATCH) prefetch_l2(reinterpret_cast<const uint32_t*>(r.tab) + (r.h & r.mask));   // used at the end of this byte
     return status;
   }
   Model::mix_shift(r, y);
@@ -571,7 +635,14 @@ __device__ __forceinline__ uint32_t lane_advance(const Shared& S, WarpCtx& W, La
       *reinterpret_cast<uint4*>(r.tab + r.c) = *reinterpret_cast<const uint4*>(r.row);
       lane_find(r, r.h + 16 * c8);
     }
-  } else W.hmap4 = (W.hmap4 & 0x1f0) | (((W.hmap4 & 0xf) * 2 + y) & 0xf);
+  } else {
+    W.hmap4 = (W.hmap4 & 0x1f0) | (((W.hmap4 & 0xf) * 2 + y) & 0xf);
+    if (c8 >= 4 && c8 < 8 && hashed) {
+      // two bits of the first nibble are known: pull the four rows the second nibble may use into L2
+#pragma unroll
+      for (uint32_t q = 0; q < 4; ++q) prefetch_l2(r.tab + (((r.h + 16u * ((uint32_t)c8 * 4u + q)) * 16u) & r.mask));
+    }
+  }
   W.c8 = c8;
   return status;
 }
@@ -584,7 +655,8 @@ __device__ __forceinline__ void lane_begin(const CodecParams& P, const Shared& S
   __syncwarp();
   r.cxt = r.c = r.ma = r.mb = r.mpos = r.h = 0;
   r.t0 = r.t1 = 0;
-  for (int k = 0; k < kMixRegs; ++k) { r.mw[k] = r.mn0[k] = r.mn1[k] = 0; W.mixh[k] = 0; }
+  for (int k = 0; k < kMixRegs; ++k) { r.mw[k] = r.mn0[k] = r.mn1[k] = 0; r.moff[k] = r.mo0[k] = r.mo1[k] = 0; W.mixh[k] = 0; }
+  r.mbyte = 0; r.mbit = 0;
   r.p = r.type == C_CONS ? ((int)r.a1 - 128) * 4 : 0;
   if (r.type == C_MATCH) r.tab2[0] = 1;                         // Predictor.cs:118
   W.arena = w.arena; W.H = w.H; W.hmask = w.hmask; W.c8 = 1; W.hmap4 = 1;

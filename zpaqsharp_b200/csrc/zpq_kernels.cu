@@ -75,7 +75,7 @@ __device__ __forceinline__ void predict_one(const Shared& S, Blk& w, int i) {
       if (c8 == 1 || (c8 & 0xf0) == 16) st[1] = find_row(ht, d.mask, d.a[0] + 2, w.H[i & w.hmask] + 16 * c8);
       const uint32_t bh = ht[st[1] + (hmap4 & 15)];
       st[0] = bh;
-      pr = S.stretch[cm_small(d, w)[bh] >> 8];
+      pr = S.stretch[cm_small(d, w)[bh * 2] >> 8];
       break;
     }
     case C_MATCH: {
@@ -135,7 +135,7 @@ __device__ __forceinline__ void update_one(const Shared& S, Blk& w, int i, int y
     case C_ICM: {
       uint8_t* slot = w.arena + d.tab + st[1] + (w.hmap4 & 15);
       *slot = S.ns[*slot * 4 + y];
-      uint32_t* cm = cm_small(d, w) + st[0];
+      uint32_t* cm = cm_small(d, w) + st[0] * 2;
       const uint32_t pn = *cm;
       *cm = pn + (uint32_t)(((int)(y * 32767 - (pn >> 8))) >> 2);
       break;

@@ -158,6 +158,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   pl.smem_p = stake(4u * nn);
   pl.smem_st = stake(20u * nn);
   pl.smem_rows = stake(512);
+  pl.smem_chain = stake(256);
   const uint64_t hbytes = 4ull << h.hh;
   if (h.n > 0 && hbytes <= 2048 && slice + hbytes <= smem_budget) { pl.smem_h = stake((uint32_t)hbytes); fill(pl.smem_h, hbytes, 0, 0, true); }
   else { pl.smem_h = kNoSmem; pl.off_h = take(hbytes); fill(pl.off_h, hbytes, 0, 0, false); }
@@ -192,8 +193,8 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (bits > 26) throw Failure(ZPQ_E_CONFIG, "max size for ICM is 26");
         d.mask = (uint32_t)((64ull << bits) - 16);
         d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false);
-        if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 1, 0, true); }
-        else { d.tab2 = take(1024); fill(d.tab2, 1024, 1, 0, false); }
+        if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 1, 0, true); }
+        else { d.tab2 = take(2048); fill(d.tab2, 2048, 1, 0, false); }
         break;
       case C_MATCH:
         if (bits > 32 || cp[2] > 32) throw Failure(ZPQ_E_CONFIG, "max size for MATCH is 32 32");

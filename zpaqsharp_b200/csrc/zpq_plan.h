@@ -80,6 +80,7 @@ struct Plan {
   int32_t nmix, maxlevel;
   uint32_t smem_rows;           // slice offset of the 32 x 16-byte hash-row cache
   uint32_t smem_m;              // slice offset of the HCOMP M array when it is small, else kNoSmem
+  uint32_t smem_chain;          // slice offset of 32 x {w0, w1*64} slots for warp-evaluated ISSE chains
   MixDesc mix[kMaxMix];
   CompDesc comp[kMaxComp];
   uint8_t order[kMaxComp];      // components sorted by (level, coop)
