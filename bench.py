@@ -316,7 +316,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_zpaq_encode_lanes", "kernel_ms": k_ms,
+                "traffic": traffic, "kernel": st.kernel.decode(errors="replace"), "kernel_ms": k_ms,
                 "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "note": "latency-bound: one dependent predict/code/update chain per warp; see DESIGN.md"}
