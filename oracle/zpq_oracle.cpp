@@ -834,9 +834,9 @@ struct LZ {
   Bytes& out; U32 bits; unsigned nbits;
 
   LZ(const U8* src, unsigned n_, const int args[9], Bytes& out_) : n(n_), out(out_), bits(0), nbits(0) {
-    inbuf.assign((size_t)n + 64, 0);
-    if (n) memcpy(inbuf.data(), src, n);
-    in = inbuf.data();
+    inbuf.assign((size_t)n + 65, 0);   // one zero in front, 64 behind: reads just outside the block are defined as 0
+    if (n) memcpy(inbuf.data() + 1, src, n);
+    in = inbuf.data() + 1;
     level = args[1] & 3;
     minMatch = args[2]; minMatch2 = args[3];
     maxMatch = (1 << 14) * 3; maxLiteral = (1 << 14) / 4;
@@ -849,7 +849,7 @@ struct LZ {
     useSA = (args[5] - args[0] >= 21);
     checkbits = !useSA ? 12 - args[0] : 17 + args[0];
     if ((minMatch < 4 && level == 1) || (minMatch < 1 && level == 2)) fail("match length $3 too small");
-    if (args[1] > 4) e8e9(inbuf.data(), (int)n);  // LZBuffer.cs:198
+    if (args[1] > 4) e8e9(inbuf.data() + 1, (int)n);  // LZBuffer.cs:198
     if (useSA || level == 3) suffix_array(in, (int)n, sa);
     if (level < 3) {
       if (useSA) isa.assign((size_t)1 << 17 << args[0], 0);

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ARCHIVES = json.load(open(os.path.join(HERE, "golden", "oracle_archives.json")))
-DEVICE_PREPROC = {"c2b_lz77_sa", "c2c_lz77_cm", "c3_bwt", "m1_lz77_hash", "e8e9_bwt"}  # LZ77/BWT encode: not on device yet
+DEVICE_PREPROC = set()   # every pre-processor (E8E9, LZ77 hash / suffix array, BWT) runs on the device
 
 
 def _input(case):
@@ -42,13 +42,33 @@ def test_encode_matches_golden_archives(gpu_ctx, case):
     assert hashlib.sha1(arc.tobytes()).hexdigest() == case["archive_sha1"]
 
 
-@pytest.mark.parametrize("case", [c for c in ARCHIVES if c["name"] in DEVICE_PREPROC],
-                         ids=[c["name"] for c in ARCHIVES if c["name"] in DEVICE_PREPROC])
-def test_encode_with_lz77_bwt_is_refused_not_faked(gpu_ctx, zlib_, case):
-    data = _input(case)
-    with pytest.raises(zlib_.ZpaqError) as e:
-        gpu_ctx.compress_blocks(data, np.asarray([0, len(data)], dtype=np.uint64), case["arg"])
-    assert e.value.code == zlib_.E_UNSUPPORTED
+@pytest.mark.parametrize("method", ["1", "2", "3", "30,128,1", "11,60,0", "11,100,2", "21,40,0", "x0,5,4,0,3,19", "x0,6,8,0,5,18c0,0,511",
+                                    "x0,7ci1", "x0,3ci1", "x0,1,4,2,3,16,1", "x0,2,3,5,2,17,2c0,0,511i1", "x0,1,4,0,7,21,2",
+                                    "x0,2,12,0,7,21,1c0,0,511i2", "x0,2,1,0,2,15", "x0,1,6,0,1,12"])
+def test_lz77_bwt_preprocessing_matches_oracle(gpu_ctx, oracle, method):
+    # LZBuffer.cs:151-486 on the device: hash-table and suffix-array matchers, both code formats, BWT, +E8E9
+    from tools import synth
+    data = synth.blocks("mixed", 600, 1, 200000).tobytes()
+    cuts = [0, 70000, 70001, 70001, 200000]
+    offs = np.asarray(cuts, dtype=np.uint64)
+    arc, ooff = gpu_ctx.compress_blocks(data, offs, method)
+    ref = b"".join(oracle.compress_block(data[cuts[i]:cuts[i + 1]], method) for i in range(len(cuts) - 1))
+    assert arc.tobytes() == ref
+    out, _, sha, _ = gpu_ctx.decompress_blocks(arc, ooff)
+    assert out.tobytes() == data and set(sha.tolist()) == {1}
+
+
+@pytest.mark.parametrize("kind,method", [("text", "2"), ("text", "3"), ("mixed", "1"), ("text", "30,128,1")])
+def test_preprocessing_full_size_blocks(gpu_ctx, oracle, kind, method):
+    from tools import synth
+    nb = 3
+    data = synth.blocks(kind, 700, nb, synth.BLOCK_1MB)
+    offs = np.arange(0, (nb + 1) * synth.BLOCK_1MB, synth.BLOCK_1MB, dtype=np.uint64)
+    arc, ooff = gpu_ctx.compress_blocks(data, offs, method)
+    ref0 = oracle.compress_block(data[:synth.BLOCK_1MB].tobytes(), method)
+    assert arc[:int(ooff[1])].tobytes() == ref0
+    out, _, sha, _ = gpu_ctx.decompress_blocks(arc, ooff)
+    assert np.array_equal(out, data) and set(sha.tolist()) == {1}
 
 
 @pytest.mark.parametrize("level", [1, 2, 3])

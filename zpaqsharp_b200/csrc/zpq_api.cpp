@@ -94,7 +94,7 @@ struct Device {
   int sms = 0;
   uint32_t smem_optin = 0;
   Tables* d_tab = nullptr;
-  DevBuf arena, in, work, slots, out, meta, plan;
+  DevBuf arena, in, work, pre, slots, out, meta, plan;
   Timer t_all, t_h2d, t_kern, t_codec, t_d2h;
   zpq_stats stats{};
 
@@ -116,7 +116,7 @@ struct Device {
   }
   void fini() {
     cudaSetDevice(id);
-    arena.release(); in.release(); work.release(); slots.release(); out.release(); meta.release(); plan.release();
+    arena.release(); in.release(); work.release(); pre.release(); slots.release(); out.release(); meta.release(); plan.release();
     if (d_tab) cudaFree(d_tab);
     t_all.fini(); t_h2d.fini(); t_kern.fini(); t_codec.fini(); t_d2h.fini();
     if (own) cudaStreamDestroy(own);
@@ -268,9 +268,13 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   d.t_all.start(s);
 
   const int pre = M.args[1];
-  if (pre != 0 && pre != 4)
-    throw Failure(ZPQ_E_UNSUPPORTED, "LZ77/BWT pre-processing (method argument 2 = " + std::to_string(pre) +
-                                         ") is not available in this build");
+  if (pre < 0 || pre > 7) throw Failure(ZPQ_E_CONFIG, "Unsupported method");
+  const int lz_level = pre & 3;                       // 0 none, 1 bit-packed LZ77, 2 byte LZ77, 3 BWT   (LibZPAQ.cs:301-312)
+  const bool do_e8 = pre >= 4;
+  const bool use_sa = lz_level == 3 || (lz_level && M.args[5] - M.args[0] >= 21);
+  if (lz_level == 1 && M.args[2] < 4) throw Failure(ZPQ_E_CONFIG, "match length $3 too small");
+  if (lz_level == 2 && M.args[2] < 1) throw Failure(ZPQ_E_CONFIG, "match length $3 too small");
+  if (lz_level && lz_level < 3 && !use_sa && (M.args[5] < 1 || M.args[5] > 28)) throw Failure(ZPQ_E_UNSUPPORTED, "LZ77 hash table size out of range");
 
   // ---- host-side metadata: preamble, prefixes, jobs ----
   Bytes preamble;
@@ -284,7 +288,8 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   Bytes prefix;
   std::vector<uint32_t> prefix_off(nb + 1);
   std::vector<EncJob> jobs(nb);
-  std::vector<uint64_t> slot_off(nb + 1), rel_off(nb);
+  std::vector<uint64_t> slot_off(nb + 1), rel_off(nb + 1), pre_off(nb + 1);
+  uint64_t pre_total = 0, max_block = 0;
   std::vector<uint32_t> lens(nb);
   uint64_t slots_total = 0, max_frame = 0;
   for (uint32_t i = 0; i < nb; ++i) {
@@ -294,11 +299,14 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
     const std::string& cm = T.comments.size() > i && !T.comments[i].empty() ? T.comments[i] : std::to_string(n);
     build_prefix(M, T.filenames.size() > i ? T.filenames[i] : std::string(), cm, T.with_tag, prefix);
     const uint32_t plen = (uint32_t)prefix.size() - prefix_off[i];
-    const uint64_t stream = n + preamble.size();
+    const uint64_t tlen = lz_level == 3 ? n + 5 : lz_level ? n + n / 16 + 64 : n;      // bound of the transformed stream
+    pre_off[i] = pre_total; pre_total = align_up(pre_total + tlen + 16, 16);
+    const uint64_t stream = tlen + preamble.size();
     const uint64_t cap = M.hdr.n ? stream + stream / 4 + 4096 : stream + 4 * (stream / 65536 + 1) + 16;
     slot_off[i] = slots_total;
-    jobs[i].in_off = off[i] - in_base;
-    jobs[i].in_len = (uint32_t)n;
+    jobs[i].in_off = lz_level ? pre_off[i] : off[i] - in_base;
+    jobs[i].in_len = lz_level ? 0u : (uint32_t)n;         // filled by the pre-processing kernels
+    max_block = std::max(max_block, n);
     jobs[i].pre_len = (uint32_t)preamble.size();
     jobs[i].out_off = slots_total + plen;
     jobs[i].out_cap = cap;
@@ -310,12 +318,14 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   }
   prefix_off[nb] = (uint32_t)prefix.size();
   slot_off[nb] = slots_total;
+  rel_off[nb] = in_total;
+  pre_off[nb] = pre_total;
 
   // ---- device buffers ----
   // meta layout: jobs | slot_off | rel_off | lens | prefix_off | prefix | preamble | results | digests | frame_len | frame_off | queue
   uint64_t mo = 0;
   auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
-  const uint64_t o_jobs = place(sizeof(EncJob) * nb), o_slot = place(8ull * (nb + 1)), o_rel = place(8ull * nb),
+  const uint64_t o_jobs = place(sizeof(EncJob) * nb), o_slot = place(8ull * (nb + 1)), o_rel = place(8ull * (nb + 1)), o_preoff = place(8ull * (nb + 1)),
                  o_len = place(4ull * nb), o_poff = place(4ull * (nb + 1)), o_prefix = place(prefix.size()),
                  o_pre = place(preamble.size()), o_res = place(sizeof(BlockResult) * nb), o_dig = place(20ull * nb),
                  o_flen = place(8ull * nb), o_foff = place(8ull * (nb + 1)), o_queue = place(256);
@@ -325,7 +335,9 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   if (T.d_in_ext) d_in = T.d_in_ext + in_base;
   else { reserve_io(d.in, std::max<uint64_t>(in_total, 16), d.arena); d_in = d.in.as<uint8_t>(); }
   uint8_t* d_work = nullptr;  // pre-processed copy when the transform must not touch the caller's data
-  if (pre == 4 && T.d_in_ext) { reserve_io(d.work, std::max<uint64_t>(in_total, 16), d.arena); d_work = d.work.as<uint8_t>(); }
+  if (do_e8 && T.d_in_ext) { reserve_io(d.work, std::max<uint64_t>(in_total, 16), d.arena); d_work = d.work.as<uint8_t>(); }
+  uint8_t* d_pre = nullptr;   // transformed streams (LZ77 / BWT output)
+  if (lz_level) { reserve_io(d.pre, std::max<uint64_t>(pre_total, 16), d.arena); d_pre = d.pre.as<uint8_t>(); }
   reserve_io(d.slots, std::max<uint64_t>(slots_total, 16), d.arena);
   uint8_t* d_out = T.d_out_ext;
   if (!d_out) { reserve_io(d.out, std::max<uint64_t>(slots_total, 16), d.arena); d_out = d.out.as<uint8_t>(); }
@@ -342,6 +354,24 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
     plan_launch(d, M.hdr, false, nb, 1ull << 30, ctx->max_resident, L);
     d.arena.reserve(std::max<uint64_t>((uint64_t)L.resident * L.plan->arena_bytes, 4096));
   }
+  // The state arenas are idle until the coding kernel starts, so the pre-processing scratch
+  // (suffix-array workspace, SA / ISA, LZ77 hash tables) lives in the same memory.
+  const uint64_t ht_entries = (lz_level == 1 || lz_level == 2) && !use_sa ? (1ull << M.args[5]) : 0;
+  auto scratch_for = [&](uint64_t bytes, uint64_t blocks) -> uint64_t {
+    uint64_t need = 4096;
+    if (use_sa) need += sa_workspace_bytes(bytes) + 8 * bytes + 1024;      // workspace + SA + ISA
+    need += ht_entries * 4 * blocks;
+    return need;
+  };
+  if (lz_level) {
+    const uint64_t want = scratch_for(in_total, nb);
+    if (d.arena.cap < want) {
+      const uint64_t fr = free_device_memory() + d.arena.cap;
+      const uint64_t reserve = 512ull << 20;
+      const uint64_t can = fr > reserve ? fr - reserve : 0;
+      if (std::min(want, can) > d.arena.cap) d.arena.reserve(std::min(want, can));
+    }
+  }
   d.plan.reserve(sizeof(Plan));
   CU(cudaMemcpyAsync(d.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
                      cudaMemcpyHostToDevice, s));
@@ -353,7 +383,8 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   };
   up(o_jobs, jobs.data(), sizeof(EncJob) * nb);
   up(o_slot, slot_off.data(), 8ull * (nb + 1));
-  up(o_rel, rel_off.data(), 8ull * nb);
+  up(o_rel, rel_off.data(), 8ull * (nb + 1));
+  up(o_preoff, pre_off.data(), 8ull * (nb + 1));
   up(o_len, lens.data(), 4ull * nb);
   up(o_poff, prefix_off.data(), 4ull * (nb + 1));
   up(o_prefix, prefix.data(), prefix.size());
@@ -373,12 +404,69 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
     ++launches;
   }
   const uint8_t* d_coded_in = d_in;
-  if (pre == 4) {  // E8E9 after the checksum, LibZPAQ.cs:307-310
+  if (do_e8) {  // E8E9 after the checksum, LibZPAQ.cs:307-310 / LZBuffer.cs:198
     uint8_t* tgt = d_work ? d_work : const_cast<uint8_t*>(d_in);
     if (d_work) CU(cudaMemcpyAsync(d_work, d_in, in_total, cudaMemcpyDeviceToDevice, s));
     CU(launch_e8e9(tgt, (const uint64_t*)(meta + o_rel), (const uint32_t*)(meta + o_len), nb, s));
     d_coded_in = tgt;
     ++launches;
+  }
+  if (lz_level) {
+    // chunks of consecutive blocks whose scratch fits in the arena memory
+    const uint8_t* src = d_coded_in;
+    uint32_t b0 = 0;
+    while (b0 < nb) {
+      uint32_t b1 = b0;
+      uint64_t bytes = 0;
+      while (b1 < nb) {
+        const uint64_t nbytes = bytes + (off[b1 + 1] - off[b1]);
+        if (b1 > b0 && (scratch_for(nbytes, b1 + 1 - b0) > d.arena.cap || nbytes >= (1ull << 32) - 4096)) break;
+        bytes = nbytes; ++b1;
+      }
+      if (scratch_for(bytes, b1 - b0) > d.arena.cap) throw Failure(ZPQ_E_NOMEM, "pre-processing scratch does not fit in device memory");
+      uint8_t* scratch = d.arena.as<uint8_t>();
+      uint64_t so = 0;
+      auto stake = [&](uint64_t n) { uint8_t* q = scratch + so; so = align_up(so + n, 256); return q; };
+      uint32_t* sa = nullptr; uint32_t* isa = nullptr;
+      const uint8_t* chunk_in = src + rel_off[b0];
+      const uint64_t* chunk_off = (const uint64_t*)(meta + o_rel) + b0;
+      uint64_t chunk_max = 0;
+      for (uint32_t b = b0; b < b1; ++b) chunk_max = std::max<uint64_t>(chunk_max, off[b + 1] - off[b]);
+      if (use_sa) {
+        sa = (uint32_t*)stake(4 * bytes);
+        isa = lz_level == 3 ? nullptr : (uint32_t*)stake(4 * bytes);
+        const size_t wsb = sa_workspace_bytes(bytes);
+        void* ws = stake(wsb);
+        int rounds = 0;
+        CU(build_suffix_arrays(chunk_in, chunk_off, b1 - b0, bytes, chunk_max, sa, isa, ws, wsb, s, &rounds));
+        launches += 3 + 5 * rounds;
+      }
+      if (lz_level == 3) {
+        CU(launch_bwt_emit(chunk_in, chunk_off, sa, (const uint64_t*)(meta + o_preoff) + b0, d_pre, (EncJob*)(meta + o_jobs) + b0,
+                           b1 - b0, chunk_max, s));
+      } else {
+        LzParams Z{};
+        Z.in = chunk_in; Z.off = chunk_off; Z.out = d_pre; Z.out_off = (const uint64_t*)(meta + o_preoff) + b0;
+        Z.jobs = (EncJob*)(meta + o_jobs) + b0;
+        Z.ht = ht_entries ? (uint32_t*)stake(ht_entries * 4 * (b1 - b0)) : nullptr;
+        Z.sa = sa; Z.isa = isa; Z.nb = b1 - b0; Z.htsize = (uint32_t)ht_entries;
+        Z.level = lz_level; Z.use_sa = use_sa ? 1 : 0;
+        Z.checkbits = use_sa ? 17 + M.args[0] : 12 - M.args[0];
+        if (Z.checkbits < 0 || Z.checkbits > 31) throw Failure(ZPQ_E_UNSUPPORTED, "LZ77 check bits out of range");
+        Z.minMatch = M.args[2]; Z.minMatch2 = M.args[3];
+        Z.maxMatch = (1u << 14) * 3; Z.maxLiteral = (1u << 14) / 4;
+        Z.lookahead = M.args[6];
+        Z.bucket = (1u << M.args[4]) - 1;
+        Z.shift1 = Z.minMatch > 0 ? (M.args[5] - 1) / Z.minMatch + 1 : 1;
+        Z.shift2 = Z.minMatch2 > 0 ? (M.args[5] - 1) / Z.minMatch2 + 1 : 0;
+        Z.minMatchBoth = std::max(Z.minMatch, Z.minMatch2 + Z.lookahead) + 4;
+        Z.rb = M.args[0] > 4 ? M.args[0] - 4 : 0;
+        CU(launch_lz77(Z, s));
+      }
+      ++launches;
+      b0 = b1;
+    }
+    d_coded_in = d_pre;
   }
   CodecParams P{};
   P.plan = d.plan.as<Plan>();

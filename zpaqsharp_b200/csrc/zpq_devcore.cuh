@@ -698,6 +698,10 @@ __device__ __forceinline__ void encode_lanes_body(const CodecParams& P, uint8_t*
     const uint64_t total = (uint64_t)J.pre_len + J.in_len;
     uint64_t opos = 0;
     uint32_t status = BLK_OK;
+    if (J.in_len == 0xFFFFFFFFu) {   // the pre-processing stage overflowed its slot
+      if (lane == 0) { P.results[job].out_len = 0; P.results[job].status = BLK_OVERFLOW; }
+      continue;
+    }
     lane_begin<Model>(P, S, w, W, r, vm, env, lane);
     uint32_t low = 1, high = 0xFFFFFFFFu;
 #define ZPQ_NORMALISE()                                                       \

@@ -40,4 +40,29 @@ cudaError_t launch_scan(const uint64_t* len, uint64_t* off, uint32_t nb, cudaStr
 cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const uint64_t* len, uint8_t* dst,
                           const uint64_t* dst_off, uint64_t dst_cap, uint32_t nb, uint64_t max_len, cudaStream_t s);
 
+// ---- pre-processing (zpq_preproc.cu) ----
+size_t sa_workspace_bytes(uint64_t n_total);
+// Suffix arrays (block-local positions) and optionally inverse suffix arrays of every block of a
+// batch; d_off = nb+1 offsets (only differences to d_off[0] matter), `in` = first byte of block 0.
+cudaError_t build_suffix_arrays(const uint8_t* in, const uint64_t* d_off, uint32_t nb, uint64_t n_total, uint64_t max_len,
+                                uint32_t* sa, uint32_t* isa, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                                int* rounds_out);
+cudaError_t launch_bwt_emit(const uint8_t* in, const uint64_t* d_off, const uint32_t* sa, const uint64_t* d_out_off, uint8_t* out,
+                            EncJob* jobs, uint32_t nb, uint64_t max_len, cudaStream_t s);
+
+struct LzParams {            // LZBuffer constructor arguments, LZBuffer.cs:151-222
+  const uint8_t* in;         // first byte of block 0 of this launch
+  const uint64_t* off;       // nb+1 input offsets
+  uint8_t* out;              // transformed streams
+  const uint64_t* out_off;   // nb+1 output slot offsets
+  EncJob* jobs;              // jobs[b].in_len receives the stream length (0xFFFFFFFF = slot overflow)
+  uint32_t* ht;              // hash tables, nb * htsize entries (hash matcher)
+  const uint32_t* sa;        // suffix arrays / inverse suffix arrays (suffix-array matcher)
+  const uint32_t* isa;
+  uint32_t nb, htsize;
+  int level, use_sa, checkbits;
+  uint32_t minMatch, minMatch2, maxMatch, maxLiteral, lookahead, bucket, shift1, shift2, minMatchBoth, rb;
+};
+cudaError_t launch_lz77(const LzParams& p, cudaStream_t s);
+
 }  // namespace zpq

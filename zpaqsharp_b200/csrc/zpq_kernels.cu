@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_encode(const CodecParam
     const uint64_t total = (uint64_t)J.pre_len + J.in_len;
     uint64_t opos = 0;
     uint32_t status = ZPQ_BLOCK_OK;
+    if (J.in_len == 0xFFFFFFFFu) {   // the pre-processing stage overflowed its slot
+      if (lane == 0) { P.results[job].out_len = 0; P.results[job].status = ZPQ_BLOCK_OVERFLOW; }
+      continue;
+    }
 
     if (S.n == 0) {
       // stored mode (Encoder.cs:58-72): [len32 BE][bytes] per 64 KB of the stream
