@@ -5,14 +5,15 @@
 namespace zpq {
 
 struct SpecKernels {
-  const void* enc = nullptr;   // __global__ function pointer (ahead of time) or cudaKernel_t (NVRTC)
+  const void* enc = nullptr;   // __global__ function pointer (ahead of time) or cudaKernel_t (NVRTC); time-skewed when the model allows
+  const void* enc_lanes = nullptr;   // encoder that walks bit by bit (huge blocks, A/B measurements)
   const void* dec = nullptr;
   const char* origin = "";     // "aot2 (HCOMP compiled)", "nvrtc", ...
 };
 
 // Ahead-of-time kernels register themselves at library load (generated files zpq_gen_aot*.cu).
 struct AotRegistrar {
-  AotRegistrar(const unsigned char* header, size_t len, const void* enc, const void* dec, const char* origin);
+  AotRegistrar(const unsigned char* header, size_t len, const void* enc, const void* enc_lanes, const void* dec, const char* origin);
 };
 
 }  // namespace zpq

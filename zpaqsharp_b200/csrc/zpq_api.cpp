@@ -138,13 +138,15 @@ struct Launch {
   uint32_t resident;
   SpecKernels spec;        // specialised kernels for this header, if any
   bool has_spec = false;
+  bool skewed = false;     // encode with the time-skewed kernel (zpq_pipe.cuh)
   std::string kernel;      // what will run (for zpq_stats)
 };
 
 cudaError_t launch_codec(const Launch& L, const CodecParams& p, bool decode, cudaStream_t s) {
   if (L.has_spec) {
     void* args[] = {const_cast<CodecParams*>(&p)};
-    return cudaLaunchKernel(decode ? L.spec.dec : L.spec.enc, dim3(L.geom.grid), dim3(L.geom.warps_per_cta * 32), args, p.sm.total, s);
+    const void* k = decode ? L.spec.dec : (L.skewed ? L.spec.enc : L.spec.enc_lanes);
+    return cudaLaunchKernel(k, dim3(L.geom.grid), dim3(L.geom.warps_per_cta * 32), args, p.sm.total, s);
   }
   return decode ? launch_decode(p, L.geom, s) : launch_encode(p, L.geom, s);
 }
@@ -165,9 +167,10 @@ uint32_t common_smem(const Plan& pl, SmemLayout& L) {
 bool force_generic();
 
 void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint64_t mem_for_arenas, uint32_t max_resident,
-                 Launch& L) {
+                 Launch& L, bool want_skew = false) {
   L.plan.reset(new Plan);
   build_plan(hdr, decode, 48 * 1024, *L.plan);
+  L.skewed = false;
   uint64_t fit = mem_for_arenas / std::max<uint64_t>(L.plan->arena_bytes, 1);
   if (fit < 1) throw Failure(ZPQ_E_NOMEM, "model state does not fit in device memory");
   uint64_t resident = std::min<uint64_t>({want, fit, (uint64_t)d.sms * 16});
@@ -175,12 +178,27 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
   if (resident < 1) resident = 1;
   uint32_t W = (uint32_t)((resident + d.sms - 1) / d.sms);
   W = std::max(1u, std::min(16u, W));
+  SpecKernels spec;
+  std::string why;
+  const bool lanes = L.plan->lane_ok && !force_generic();
+  const bool has_spec = lanes && find_spec_kernels(hdr, d.smem_optin, spec, &why);
+  if (want_skew && has_spec && !decode) {
+    // The time-skewed encoder (zpq_pipe.cuh) keeps every ICM/ISSE map in the block's shared slice:
+    // take the largest number of blocks per SM for which that holds.
+    for (uint32_t w = W; w >= 1 && !L.skewed; --w) {
+      const uint32_t common = common_smem(*L.plan, L.sm);
+      const uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
+      build_plan(hdr, decode, (avail / w) & ~127u, *L.plan);
+      if (L.plan->pipe_ok && L.plan->pipe_maps && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.skewed = true; W = w; }
+    }
+    if (!L.skewed) build_plan(hdr, decode, 48 * 1024, *L.plan);
+  }
   for (;;) {
     uint32_t common = common_smem(*L.plan, L.sm);
     uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
     if ((uint64_t)W * L.plan->smem_warp_bytes <= avail) break;
     uint32_t budget = avail / W;
-    uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64 + 512 + 256, 128);
+    uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64 + 1024 + 256, 128) + (hdr.n <= 32 ? 4096u : 0u);
     if (budget >= minimal) {
       build_plan(hdr, decode, budget & ~127u, *L.plan);
       common = common_smem(*L.plan, L.sm);
@@ -195,14 +213,12 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
   L.sm.slice_bytes = L.plan->smem_warp_bytes;
   L.sm.total = L.sm.slices + W * L.sm.slice_bytes;
   L.geom.warps_per_cta = W;
-  L.geom.lanes = (L.plan->lane_ok && !force_generic()) ? 1u : 0u;
-  L.has_spec = false;
+  L.geom.lanes = lanes ? 1u : 0u;
+  L.has_spec = has_spec;
+  L.spec = spec;
   L.kernel = L.geom.lanes ? "lanes/generic" : "steps/generic";
-  if (L.geom.lanes) {
-    std::string why;
-    if (find_spec_kernels(hdr, d.smem_optin, L.spec, &why)) { L.has_spec = true; L.kernel = std::string("lanes/") + L.spec.origin; }
-    else L.kernel += " (" + why.substr(0, 60) + ")";
-  }
+  if (has_spec) L.kernel = std::string("lanes/") + spec.origin + (L.skewed ? ", time-skewed" : "");
+  else if (lanes) L.kernel += " (" + why.substr(0, 60) + ")";
   L.geom.grid = (uint32_t)((resident + W - 1) / W);
   L.resident = (uint32_t)resident;
 }
@@ -348,7 +364,11 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   if (M.hdr.n) {
     const uint64_t fr = free_device_memory() + d.arena.cap;
     const uint64_t reserve = 512ull << 20;
-    plan_launch(d, M.hdr, false, nb, fr > reserve ? fr - reserve : 0, ctx->max_resident, L);
+    // time-skewed encoder: every lane model whose coder delay fits (zpq_pipe.cuh); ZPQ_PIPE=0 keeps the
+    // bit-by-bit lane encoder (A/B measurements); blocks of 2^28 bytes and more overflow its bit counter
+    const char* e = getenv("ZPQ_PIPE");
+    const bool want_skew = !(e && *e == '0') && max_block + max_block / 16 + preamble.size() + 64 < (1ull << 28);
+    plan_launch(d, M.hdr, false, nb, fr > reserve ? fr - reserve : 0, ctx->max_resident, L, want_skew);
     d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
   } else {
     plan_launch(d, M.hdr, false, nb, 1ull << 30, ctx->max_resident, L);

@@ -161,7 +161,7 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   o << "// Generated by zpq_codegen from block header";
   for (size_t i = 0; i < hdr.wire.size() && i < 48; ++i) { char b[8]; snprintf(b, sizeof b, " %02x", hdr.wire[i]); o << b; }
   o << (hdr.wire.size() > 48 ? " ...\n" : "\n");
-  o << "#include \"zpq_devcore.cuh\"\nnamespace zpq {\nstruct " << name << " {\n";
+  o << "#include \"zpq_pipe.cuh\"\nnamespace zpq {\nstruct " << name << " {\n";
 
   uint32_t tmask[10] = {0};
   for (int i = 0; i < pl.n; ++i) tmask[pl.comp[i].type] |= 1u << i;
@@ -296,8 +296,48 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   } else {
     o << "    return GenericModel::hcomp(S, W, vm, env, input, lane);\n";
   }
-  o << "  }\n};\n}  // namespace zpq\n\n";
+  o << "  }\n};\n";
+
+  // ---- time-skewed encoder policy (zpq_pipe.cuh) ----
+  if (pl.pipe_ok) {
+    o << "struct Pipe_" << name << " {\n"
+      << "  static constexpr int D = " << pl.coder_delay << ", N = " << pl.n << ", RS = " << pl.ring_slots << ", RSTRIDE = " << pl.ring_stride << ";\n";
+    for (int k = 0; k < pl.nmix; ++k)
+      if (mix_regs)
+        o << "  typedef MixPipe<" << k << ", " << (int)pl.mix[k].lane << ", " << (int)pl.mix[k].j0 << ", " << (int)pl.mix[k].m << ", "
+          << (int)pl.mix[k].rate << ", " << pl.mix[k].mask << "u, " << (int)pl.mix[k].cmask << "u, " << (int)pl.comp[pl.mix[k].lane].delay
+          << "> PMix" << k << ";\n";
+    o << "  static __device__ __forceinline__ void lead0(const Shared& S, const PipeCtx& W, LaneRegs& r, int lane, int k, int y) {\n";
+    if (tmask[C_CM]) o << "    if (" << lane_test(tmask[C_CM]) << ") pipe_cm(S, W, r, lane, y);\n";
+    if (tmask[C_MATCH]) o << "    if (" << lane_test(tmask[C_MATCH]) << ") pipe_match(S, W, r, lane, k, y);\n";
+    o << "  }\n";
+    o << "  template <bool CHECKED> static __device__ __forceinline__ void lag(const Shared& S, const PipeCtx& W, LaneRegs& r, int lane) {\n";
+    if (tmask[C_ICM] | tmask[C_ISSE]) o << "    pipe_icm_isse<CHECKED>(S, W, r, lane);   // branch-free on all lanes\n";
+    if (tmask[C_AVG]) o << "    if (" << lane_test(tmask[C_AVG]) << ") pipe_avg<CHECKED>(W, r, lane);\n";
+    if (tmask[C_MIX2]) o << "    if (" << lane_test(tmask[C_MIX2]) << ") pipe_mix2<CHECKED>(S, W, r, lane);\n";
+    if (tmask[C_SSE]) o << "    if (" << lane_test(tmask[C_SSE]) << ") pipe_sse<CHECKED>(S, W, r, lane);\n";
+    o << "  }\n";
+    o << "  template <bool CHECKED> static __device__ __forceinline__ void mixes(const Shared& S, const PipeCtx& W, LaneRegs& r, int lane) {\n";
+    for (int k = 0; k < pl.nmix; ++k) {
+      if (mix_regs) o << "    PMix" << k << "::template tick<CHECKED>(S, W, r, lane);\n";
+      else o << "    pipe_mix_rt<CHECKED>(S, S.mix[" << k << "], " << (int)pl.comp[pl.mix[k].lane].delay << ", W, r, lane);\n";
+    }
+    o << "  }\n";
+    o << "  static __device__ __forceinline__ void prefetch(const PipeCtx& W, const LaneRegs& r, uint32_t hnext, uint32_t cnext, int lane) {\n";
+    for (int k = 0; k < pl.nmix; ++k)
+      if (mix_regs) o << "    PMix" << k << "::prefetch(W, r, hnext, cnext, lane);\n";
+    o << "  }\n";
+    o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane) {\n"
+      << "    return " << name << "::hcomp(S, W, vm, env, input, lane);\n  }\n};\n";
+  }
+  o << "}  // namespace zpq\n\n";
+  // <enc_kernel>: time-skewed encoder when the model allows it; <enc_kernel>_l: lane-resident encoder
+  // that walks bit by bit (blocks of 256 MB and more, A/B measurements)
   o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << enc_kernel << "(const zpq::CodecParams P) {\n"
+    << "  extern __shared__ __align__(128) uint8_t smem[];\n";
+  if (pl.pipe_ok) o << "  zpq::encode_pipe_body<zpq::Pipe_" << name << ">(P, smem);\n}\n";
+  else o << "  zpq::encode_lanes_body<zpq::" << name << ">(P, smem);\n}\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << enc_kernel << "_l(const zpq::CodecParams P) {\n"
     << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::encode_lanes_body<zpq::" << name << ">(P, smem);\n}\n";
   o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << dec_kernel << "(const zpq::CodecParams P) {\n"
     << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::decode_lanes_body<zpq::" << name << ">(P, smem);\n}\n";
@@ -322,8 +362,8 @@ int main(int argc, char** argv) {
       std::ostringstream reg;
       reg << "\n#include \"zpq_aot.h\"\nnamespace {\nconst unsigned char kHeader[] = {";
       for (size_t i = 0; i < wire.size(); ++i) reg << (int)wire[i] << (i + 1 < wire.size() ? "," : "");
-      reg << "};\nconst zpq::AotRegistrar kReg(kHeader, sizeof kHeader, (const void*)zpq_enc_" << id << ", (const void*)zpq_dec_" << id
-          << ", \"" << id << (compiled ? " (HCOMP compiled)" : " (HCOMP interpreted)") << "\");\n}\n";
+      reg << "};\nconst zpq::AotRegistrar kReg(kHeader, sizeof kHeader, (const void*)zpq_enc_" << id << ", (const void*)zpq_enc_" << id
+          << "_l, (const void*)zpq_dec_" << id << ", \"" << id << (compiled ? " (HCOMP compiled)" : " (HCOMP interpreted)") << "\");\n}\n";
       const std::string path = std::string(argv[1]) + "/zpq_gen_" + id + ".cu";
       FILE* f = fopen(path.c_str(), "w");
       if (!f) { perror(path.c_str()); return 1; }

@@ -271,6 +271,7 @@ __device__ __forceinline__ void train(const Shared& S, uint32_t* cm, uint32_t li
 // ==========================================================================================
 struct LaneRegs {
   int type, level, srcj, srck;
+  int d;              // pipelined encoder: bits this component works behind the lead (zpq_pipe.cuh)
   uint32_t a1, a2, a3, a4, a5;
   uint32_t mask, mask2;
   uint8_t* tab;
@@ -284,8 +285,8 @@ struct LaneRegs {
   int p, t0, t1;
   int2* chain;        // this lane's slot {w0, w1*64} for ISSE chains evaluated by the whole warp
   // MIX k held in registers: weight `lane` of the current row and of both possible next rows
-  int mw[kMixRegs], mn0[kMixRegs], mn1[kMixRegs];
-  uint32_t moff[kMixRegs], mo0[kMixRegs], mo1[kMixRegs];   // byte offsets of those weights in the table
+  int mw[kMixRegs], mn0[kMixRegs], mn1[kMixRegs], mn2[kMixRegs];
+  uint32_t moff[kMixRegs], mo0[kMixRegs], mo1[kMixRegs], mo2[kMixRegs];   // byte offsets of those weights in the table
   const uint8_t* mixtab[kMixRegs];
 };
 
@@ -297,7 +298,7 @@ struct WarpCtx {
 };
 
 __device__ __forceinline__ void lane_load(const Shared& S, const CodecParams& P, const Blk& w, LaneRegs& r, int lane) {
-  r.type = C_NONE; r.level = 0; r.srcj = r.srck = 0;
+  r.type = C_NONE; r.level = 0; r.srcj = r.srck = 0; r.d = 0;
   r.a1 = r.a2 = r.a3 = r.a4 = r.a5 = 0; r.mask = r.mask2 = 0;
   r.tab = r.tab2 = nullptr;
   r.cm = reinterpret_cast<uint32_t*>(const_cast<int16_t*>(S.stretch));   // readable dummy for lanes without a map
@@ -306,7 +307,7 @@ __device__ __forceinline__ void lane_load(const Shared& S, const CodecParams& P,
   for (int k = 0; k < kMixRegs; ++k) r.mixtab[k] = k < S.nmix ? w.arena + S.mix[k].tab : w.arena;
   if (lane < S.n) {
     const CompDesc& d = S.comp[lane];
-    r.type = d.type; r.level = d.level;
+    r.type = d.type; r.level = d.level; r.d = d.delay;
     r.a1 = d.a[0]; r.a2 = d.a[1]; r.a3 = d.a[2]; r.a4 = d.a[3]; r.a5 = d.a[4];
     r.mask = d.mask; r.mask2 = d.mask2;
     r.tab = w.arena + d.tab; r.tab2 = w.arena + d.tab2;

@@ -157,8 +157,38 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   const int nn = std::max(h.n, 1);
   pl.smem_p = stake(4u * nn);
   pl.smem_st = stake(20u * nn);
-  pl.smem_rows = stake(512);
+  pl.smem_rows = stake(1024);   // 32 lanes x 16-byte row cache, twice (the skewed encoder requests rows a nibble ahead)
   pl.smem_chain = stake(256);
+  // Pipelined encoder: component i works delay[i] bits behind the leading bit, strictly later than
+  // everything it reads; a MIX additionally stays kPipeMixAhead bits back so that its weight rows
+  // can be requested before they are needed.  The coder follows component n-1 by one bit.
+  uint8_t delay[kMaxComp + 1] = {0};
+  {
+    const uint8_t* q = &h.wire[7];
+    for (int i = 0; i < h.n; ++i) {
+      int dl = 0;
+      auto in = [&](int j) { if (j < i) dl = std::max(dl, delay[j] + 1); };
+      switch (q[0]) {
+        case C_AVG: in(q[1]); in(q[2]); break;
+        case C_MIX2: in(q[2]); in(q[3]); break;
+        case C_ISSE: case C_SSE: in(q[2]); break;
+        case C_MIX: for (int j = 0; j < q[3]; ++j) in(q[2] + j); dl = std::max(dl, kPipeMixAhead); break;
+        default: break;
+      }
+      delay[i] = (uint8_t)std::min(dl, 255);
+      q += comp_len(q[0]);
+    }
+    pl.coder_delay = h.n ? delay[h.n - 1] + 1 : 1;
+    pl.ring_slots = 8;
+    while ((int)pl.ring_slots <= pl.coder_delay) pl.ring_slots *= 2;
+    pl.ring_stride = (uint32_t)align_up(nn, 8);
+    pl.pipe_ok = h.n >= 1 && h.n <= 32 && pl.coder_delay <= kMaxPipeDelay;
+    if (pl.pipe_ok) {
+      pl.smem_pring = stake(2u * pl.ring_slots * pl.ring_stride);
+      pl.smem_bhring = stake(pl.ring_slots * pl.ring_stride);
+      pl.smem_hsnap = stake(4u * 8 * pl.ring_stride);
+    }
+  }
   const uint64_t hbytes = 4ull << h.hh;
   if (h.n > 0 && hbytes <= 2048 && slice + hbytes <= smem_budget) { pl.smem_h = stake((uint32_t)hbytes); fill(pl.smem_h, hbytes, 0, 0, true); }
   else { pl.smem_h = kNoSmem; pl.off_h = take(hbytes); fill(pl.off_h, hbytes, 0, 0, false); }
@@ -247,6 +277,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
       default: throw Failure(ZPQ_E_CONFIG, "unknown component type");
     }
     d.level = (uint8_t)level;
+    d.delay = delay[i];
     cp += len;
   }
 
@@ -282,6 +313,10 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   }
   pl.nsteps = ns;
   pl.maxlevel = maxlevel;
+  // the time-skewed encoder addresses the ICM/ISSE maps as shared memory
+  pl.pipe_maps = 1;
+  for (int i = 0; i < h.n; ++i)
+    if ((pl.comp[i].type == C_ICM || pl.comp[i].type == C_ISSE) && pl.comp[i].smem_cm == kNoSmem) pl.pipe_maps = 0;
   pl.nmix = 0;
   pl.lane_ok = h.n >= 1 && h.n <= 32;
   for (int i = 0; i < h.n; ++i) {

@@ -31,7 +31,8 @@ struct CompDesc {
   uint64_t tab;        // arena byte offset of the primary table (cm / ht / a16 / MATCH index)
   uint64_t tab2;       // arena byte offset of the secondary table (ICM/ISSE cm when not in smem; MATCH buffer)
   uint32_t smem_cm;    // byte offset of the ICM/ISSE cm table in the warp's shared slice, or kNoSmem
-  uint32_t pad;
+  uint8_t delay;       // pipelined encoder: this component works `delay` bits behind the leading bit
+  uint8_t pad[3];
 };
 static_assert(sizeof(CompDesc) == 40, "CompDesc layout");
 
@@ -65,6 +66,8 @@ struct MixDesc {
 };
 constexpr int kMaxMix = 16;
 constexpr int kMixRegs = 4;   // MIX components whose weights a specialised kernel keeps in registers
+constexpr int kMaxPipeDelay = 23;   // the pipelined encoder keeps the last 32 coded bits in one register
+constexpr int kPipeMixAhead = 2;    // MIX rows are loaded this many bits before they are used
 
 struct Plan {
   int32_t n;                    // components
@@ -81,6 +84,15 @@ struct Plan {
   uint32_t smem_rows;           // slice offset of the 32 x 16-byte hash-row cache
   uint32_t smem_m;              // slice offset of the HCOMP M array when it is small, else kNoSmem
   uint32_t smem_chain;          // slice offset of 32 x {w0, w1*64} slots for warp-evaluated ISSE chains
+  // pipelined encoder (zpq_pipe.cuh): rings indexed [bit time & (ring_slots-1)][component]
+  int32_t pipe_ok;              // 1: the time-skewed encoder applies (lane_ok and coder_delay <= kMaxPipeDelay)
+  int32_t pipe_maps;            // 1: with this shared-memory budget every ICM/ISSE map is in the shared slice (required at launch)
+  int32_t coder_delay;          // delay of the arithmetic coder = delay of component n-1 plus one
+  uint32_t ring_slots;          // power of two > coder_delay
+  uint32_t ring_stride;         // entries per ring slot (>= n, multiple of 8)
+  uint32_t smem_pring;          // int16 stretched predictions
+  uint32_t smem_bhring;         // uint8 bit histories of ICM/ISSE components
+  uint32_t smem_hsnap;          // uint32 contexts H[i] of the last 8 bytes (ring of 8 x ring_stride)
   MixDesc mix[kMaxMix];
   CompDesc comp[kMaxComp];
   uint8_t order[kMaxComp];      // components sorted by (level, coop)

@@ -62,10 +62,10 @@ bool specialize_enabled() {
 
 }  // namespace
 
-AotRegistrar::AotRegistrar(const unsigned char* header, size_t len, const void* enc, const void* dec, const char* origin) {
+AotRegistrar::AotRegistrar(const unsigned char* header, size_t len, const void* enc, const void* enc_lanes, const void* dec, const char* origin) {
   Registry& r = registry();
   std::lock_guard<std::mutex> g(r.mu);
-  SpecKernels k; k.enc = enc; k.dec = dec; k.origin = origin;
+  SpecKernels k; k.enc = enc; k.enc_lanes = enc_lanes; k.dec = dec; k.origin = origin;
   r.table[Bytes(header, header + len)] = k;
 }
 
@@ -74,9 +74,9 @@ Bytes nvrtc_compile(const std::string& src) {
   Nvrtc& n = nvrtc();
   if (!n.ok) throw Failure(ZPQ_E_UNSUPPORTED, "libnvrtc is not available");
   nvrtcProgram prog = nullptr;
-  const char* hdr_src[2] = {kEmbedPlan, kEmbedDevcore};
-  const char* hdr_name[2] = {"zpq_plan.h", "zpq_devcore.cuh"};
-  if (n.CreateProgram(&prog, src.c_str(), "zpq_model.cu", 2, hdr_src, hdr_name) != 0)
+  const char* hdr_src[3] = {kEmbedPlan, kEmbedDevcore, kEmbedPipe};
+  const char* hdr_name[3] = {"zpq_plan.h", "zpq_devcore.cuh", "zpq_pipe.cuh"};
+  if (n.CreateProgram(&prog, src.c_str(), "zpq_model.cu", 3, hdr_src, hdr_name) != 0)
     throw Failure(ZPQ_E_CUDA, "nvrtcCreateProgram failed");
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
   const int rc = n.CompileProgram(prog, 3, opts);
@@ -114,13 +114,14 @@ bool find_spec_kernels(const Header& hdr, uint32_t smem_limit, SpecKernels& out,
     cudaLibrary_t lib = nullptr;
     cudaError_t ce = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (ce != cudaSuccess) throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce));
-    cudaKernel_t ke = nullptr, kd = nullptr;
-    if ((ce = cudaLibraryGetKernel(&ke, lib, "zpq_enc_rt")) != cudaSuccess || (ce = cudaLibraryGetKernel(&kd, lib, "zpq_dec_rt")) != cudaSuccess)
+    cudaKernel_t ke = nullptr, kl = nullptr, kd = nullptr;
+    if ((ce = cudaLibraryGetKernel(&ke, lib, "zpq_enc_rt")) != cudaSuccess || (ce = cudaLibraryGetKernel(&kl, lib, "zpq_enc_rt_l")) != cudaSuccess ||
+        (ce = cudaLibraryGetKernel(&kd, lib, "zpq_dec_rt")) != cudaSuccess)
       throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce));
-    for (cudaKernel_t k : {ke, kd})
+    for (cudaKernel_t k : {ke, kl, kd})
       if ((ce = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit)) != cudaSuccess)
         throw Failure(ZPQ_E_CUDA, std::string("cudaFuncSetAttribute(nvrtc kernel): ") + cudaGetErrorString(ce));
-    SpecKernels k; k.enc = (const void*)ke; k.dec = (const void*)kd; k.origin = "nvrtc";
+    SpecKernels k; k.enc = (const void*)ke; k.enc_lanes = (const void*)kl; k.dec = (const void*)kd; k.origin = "nvrtc";
     r.table[hdr.wire] = k;
     out = k;
     return true;
@@ -138,6 +139,7 @@ void spec_set_smem_limit(uint32_t bytes) {
   std::lock_guard<std::mutex> g(r.mu);
   for (auto& kv : r.table) {
     cudaFuncSetAttribute(kv.second.enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (kv.second.enc_lanes) cudaFuncSetAttribute(kv.second.enc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     cudaFuncSetAttribute(kv.second.dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   }
   cudaGetLastError();
