@@ -30,7 +30,7 @@ bool find_spec_kernels(const Header& hdr, uint32_t smem_limit, SpecKernels& out,
 void spec_set_smem_limit(uint32_t bytes);
 Bytes nvrtc_compile(const std::string& src);
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
-                                  const std::string& dec_kernel, bool* compiled_hcomp);
+                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g);
 }
 
 using namespace zpq;
@@ -139,13 +139,15 @@ struct Launch {
   SpecKernels spec;        // specialised kernels for this header, if any
   bool has_spec = false;
   bool skewed = false;     // encode with the time-skewed kernel (zpq_pipe.cuh)
+  bool duo = false;        // encode with the two-role kernel (zpq_duo.cuh)
+  uint32_t wb = 0;         // ... blocks per CTA
   std::string kernel;      // what will run (for zpq_stats)
 };
 
 cudaError_t launch_codec(const Launch& L, const CodecParams& p, bool decode, cudaStream_t s) {
   if (L.has_spec) {
     void* args[] = {const_cast<CodecParams*>(&p)};
-    const void* k = decode ? L.spec.dec : (L.skewed ? L.spec.enc : L.spec.enc_lanes);
+    const void* k = decode ? L.spec.dec : L.duo ? L.spec.enc_duo : (L.skewed ? L.spec.enc : L.spec.enc_lanes);
     return cudaLaunchKernel(k, dim3(L.geom.grid), dim3(L.geom.warps_per_cta * 32), args, p.sm.total, s);
   }
   return decode ? launch_decode(p, L.geom, s) : launch_encode(p, L.geom, s);
@@ -167,10 +169,10 @@ uint32_t common_smem(const Plan& pl, SmemLayout& L) {
 bool force_generic();
 
 void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint64_t mem_for_arenas, uint32_t max_resident,
-                 Launch& L, bool want_skew = false) {
+                 Launch& L, bool want_skew = false, bool want_duo = false) {
   L.plan.reset(new Plan);
   build_plan(hdr, decode, 48 * 1024, *L.plan);
-  L.skewed = false;
+  L.skewed = false; L.duo = false; L.wb = 0;
   uint64_t fit = mem_for_arenas / std::max<uint64_t>(L.plan->arena_bytes, 1);
   if (fit < 1) throw Failure(ZPQ_E_NOMEM, "model state does not fit in device memory");
   uint64_t resident = std::min<uint64_t>({want, fit, (uint64_t)d.sms * 16});
@@ -182,6 +184,36 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
   std::string why;
   const bool lanes = L.plan->lane_ok && !force_generic();
   const bool has_spec = lanes && find_spec_kernels(hdr, d.smem_optin, spec, &why);
+  if (want_duo && has_spec && spec.enc_duo && !decode) {
+    // Two-role encoder (zpq_duo.cuh): 32/G blocks share a pair of warps, up to 7 pairs per SM plus one
+    // arithmetic coder warp (lane = block, so at most 32 blocks); every ICM/ISSE map has to live in the block's shared slice.
+    const uint32_t G = (uint32_t)spec.duo_g, B = 32 / G;
+    uint64_t res = std::min<uint64_t>({want, fit, (uint64_t)d.sms * std::min(7u * B, 32u)});
+    if (max_resident) res = std::min<uint64_t>(res, max_resident);
+    if (res < 1) res = 1;
+    uint32_t wb = (uint32_t)((res + d.sms - 1) / d.sms);
+    for (uint32_t w = wb; w >= 1 && !L.duo; --w) {
+      const uint32_t common = common_smem(*L.plan, L.sm);
+      const uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
+      build_plan(hdr, false, (avail / w) & ~127u, *L.plan, (int)G);
+      if (L.plan->duo_ok && L.plan->pipe_maps && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.duo = true; wb = w; }
+    }
+    if (L.duo) {
+      res = std::min<uint64_t>(res, (uint64_t)wb * d.sms);
+      L.sm.slices = common_smem(*L.plan, L.sm);
+      L.sm.slice_bytes = L.plan->smem_warp_bytes;
+      L.sm.total = L.sm.slices + wb * L.sm.slice_bytes;
+      L.wb = wb;
+      L.geom.warps_per_cta = 1 + 2 * ((wb + B - 1) / B);
+      L.geom.lanes = 1;
+      L.has_spec = true; L.spec = spec;
+      L.kernel = std::string("duo/") + spec.origin + ", two-role x" + std::to_string(B) + " blocks per warp pair";
+      L.geom.grid = (uint32_t)((res + wb - 1) / wb);
+      L.resident = (uint32_t)res;
+      return;
+    }
+    build_plan(hdr, decode, 48 * 1024, *L.plan);
+  }
   if (want_skew && has_spec && !decode) {
     // The time-skewed encoder (zpq_pipe.cuh) keeps every ICM/ISSE map in the block's shared slice:
     // take the largest number of blocks per SM for which that holds.
@@ -366,9 +398,13 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
     const uint64_t reserve = 512ull << 20;
     // time-skewed encoder: every lane model whose coder delay fits (zpq_pipe.cuh); ZPQ_PIPE=0 keeps the
     // bit-by-bit lane encoder (A/B measurements); blocks of 2^28 bytes and more overflow its bit counter
+    // ZPQ_DUO=0 keeps the single-warp encoders (A/B measurements)
     const char* e = getenv("ZPQ_PIPE");
-    const bool want_skew = !(e && *e == '0') && max_block + max_block / 16 + preamble.size() + 64 < (1ull << 28);
-    plan_launch(d, M.hdr, false, nb, fr > reserve ? fr - reserve : 0, ctx->max_resident, L, want_skew);
+    const char* e2 = getenv("ZPQ_DUO");
+    const bool fits = max_block + max_block / 16 + preamble.size() + 64 < (1ull << 28);
+    const bool want_skew = !(e && *e == '0') && fits;
+    const bool want_duo = !(e2 && *e2 == '0') && fits;
+    plan_launch(d, M.hdr, false, nb, fr > reserve ? fr - reserve : 0, ctx->max_resident, L, want_skew, want_duo);
     d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
   } else {
     plan_launch(d, M.hdr, false, nb, 1ull << 30, ctx->max_resident, L);
@@ -501,6 +537,7 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
   P.njobs = nb;
   P.resident = L.resident;
   P.queue = (uint32_t*)(meta + o_queue);
+  P.wb = L.wb;
   P.sm = L.sm;
   d.t_codec.start(s);
   CU(launch_codec(L, P, false, s));
@@ -1043,7 +1080,7 @@ int64_t zpq_specialize_model(const uint8_t* hdr, uint64_t hdr_len, char* source,
     Header h;
     parse_header(hdr, hdr_len, h);
     bool compiled = false;
-    src = generate_model_source(h, "Model_rt", "zpq_enc_rt", "zpq_dec_rt", &compiled);
+    src = generate_model_source(h, "Model_rt", "zpq_enc_rt", "zpq_dec_rt", &compiled, nullptr);
     Bytes cubin = nvrtc_compile(src);
     size = (int64_t)cubin.size();
     msg = compiled ? "HCOMP compiled" : "HCOMP interpreted";

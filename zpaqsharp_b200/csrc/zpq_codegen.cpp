@@ -152,7 +152,7 @@ std::string lane_test(uint32_t mask) {
 // Source of one specialised model.  `name` becomes the model struct name; the kernels are
 // extern "C" <enc_kernel> / <dec_kernel>.
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
-                                  const std::string& dec_kernel, bool* compiled_hcomp) {
+                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g) {
   std::unique_ptr<Plan> plp(new Plan);
   Plan& pl = *plp;
   build_plan(hdr, false, 48 * 1024, pl);
@@ -161,7 +161,7 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   o << "// Generated by zpq_codegen from block header";
   for (size_t i = 0; i < hdr.wire.size() && i < 48; ++i) { char b[8]; snprintf(b, sizeof b, " %02x", hdr.wire[i]); o << b; }
   o << (hdr.wire.size() > 48 ? " ...\n" : "\n");
-  o << "#include \"zpq_pipe.cuh\"\nnamespace zpq {\nstruct " << name << " {\n";
+  o << "#include \"zpq_duo.cuh\"\nnamespace zpq {\nstruct " << name << " {\n";
 
   uint32_t tmask[10] = {0};
   for (int i = 0; i < pl.n; ++i) tmask[pl.comp[i].type] |= 1u << i;
@@ -278,7 +278,8 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   std::ostringstream body;
   const bool ok = translate_zpaql(pl.hcomp, pl.hcomp_len, body);
   if (compiled_hcomp) *compiled_hcomp = ok;
-  o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane) {\n";
+  // hcomp_m: `smask` names the lanes that run this HCOMP together (the whole warp, or one block's lanes in the two-role encoder)
+  o << "  static __device__ __forceinline__ int hcomp_m(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane, uint32_t smask) {\n";
   if (ok) {
     o << "    // ZPAQL -> C, run uniformly by all lanes (every lane stores the same values)\n"
       << "    const uint32_t HMASK = " << ((1u << pl.hh) - 1) << "u, MMASK = " << (uint32_t)((1ull << pl.hm) - 1) << "u;\n"
@@ -286,16 +287,19 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
       << "    uint32_t a = input, b = vm.b, c = vm.c, d = vm.d, f = vm.f;\n"
       << "    int budget = 1 << 20, rc = 0;\n"
       << "    (void)HMASK; (void)MMASK; (void)H; (void)M; (void)R; (void)budget;\n"
-      << "    __syncwarp();\n"
+      << "    __syncwarp(smask);\n"
       << body.str()
       << "  Lerr: rc = 1;\n"
       << "  Lhalt:\n"
       << "    vm.b = b; vm.c = c; vm.d = d; vm.f = f;\n"
-      << "    __syncwarp();\n"
+      << "    __syncwarp(smask);\n"
       << "    return rc;\n";
   } else {
     o << "    return GenericModel::hcomp(S, W, vm, env, input, lane);\n";
   }
+  o << "  }\n";
+  o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane) {\n"
+    << "    return hcomp_m(S, W, vm, env, input, lane, ZPQ_FULL);\n";
   o << "  }\n};\n";
 
   // ---- time-skewed encoder policy (zpq_pipe.cuh) ----
@@ -330,7 +334,50 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
     o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane) {\n"
       << "    return " << name << "::hcomp(S, W, vm, env, input, lane);\n  }\n};\n";
   }
+  // ---- two-role encoder policy (zpq_duo.cuh) ----
+  const int G = pl.n <= 8 ? 8 : pl.n <= 16 ? 16 : 32;
+  std::unique_ptr<Plan> pdp(new Plan);
+  Plan& pd = *pdp;
+  build_plan(hdr, false, 48 * 1024, pd, G);
+  const bool duo = ok && pd.duo_ok;
+  if (duo_g) *duo_g = duo ? G : 0;
+  if (duo) {
+    uint32_t lmask = tmask[C_CONS] | tmask[C_CM] | tmask[C_ICM] | tmask[C_MATCH];
+    o << "struct Duo_" << name << " {\n"
+      << "  static constexpr int G = " << G << ", N = " << pl.n << ", D = " << pd.coder_delay << ", LDEPTH = " << pd.duo_ldepth
+      << ", HDEPTH = " << pd.duo_hdepth << ";\n"
+      << "  static constexpr unsigned LMASK = 0x" << std::hex << lmask << std::dec << "u;\n"
+      << "  static constexpr bool HAS_HASHED = " << ((tmask[C_ICM] | tmask[C_ISSE]) ? "true" : "false") << ", HAS_MATCH = " << (tmask[C_MATCH] ? "true" : "false")
+      << ", HAS_CM = " << (tmask[C_CM] ? "true" : "false") << ", HAS_CONS = " << (tmask[C_CONS] ? "true" : "false")
+      << ", HAS_ISSE = " << (tmask[C_ISSE] ? "true" : "false") << ", NEEDK = " << ((tmask[C_AVG] | tmask[C_MIX2]) ? "true" : "false")
+      << ", FINAL_MIX = " << (pl.comp[pl.n - 1].type == C_MIX ? "true" : "false") << ";\n";
+    for (int k = 0; k < pl.nmix; ++k)
+      if (mix_regs)
+        o << "  typedef MixDuo<" << G << ", " << k << ", " << (int)pl.mix[k].lane << ", " << (int)pl.mix[k].j0 << ", " << (int)pl.mix[k].m << ", "
+          << (int)pl.mix[k].rate << ", " << pl.mix[k].mask << "u, " << (int)pl.mix[k].cmask << "u, " << (int)pd.comp[pl.mix[k].lane].delay
+          << ", LMASK> QMix" << k << ";\n";
+    o << "  static __device__ __forceinline__ void lanes(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, int pj, int pk, int y, bool act, uint32_t t, int& p, int lane) {\n";
+    if (tmask[C_AVG]) o << "    if (" << lane_test(tmask[C_AVG]) << ") duo_avg<G>(r, pj, pk, act, p);\n";
+    if (tmask[C_MIX2]) o << "    if (" << lane_test(tmask[C_MIX2]) << ") duo_mix2<G>(S, C, r, pj, pk, y, act, t, p, lane);\n";
+    if (tmask[C_SSE]) o << "    if (" << lane_test(tmask[C_SSE]) << ") duo_sse<G>(S, C, r, pj, y, act, t, p, lane);\n";
+    o << "  }\n";
+    o << "  template <bool FAST, int KT> static __device__ __forceinline__ void mixes(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, const Hist& H, int& p, int& pmv, int lane, uint32_t gmask, int gbase, bool live) {\n";
+    for (int k = 0; k < pl.nmix; ++k) {
+      if (mix_regs) o << "    QMix" << k << "::template tick<FAST, KT>(S, C, r, H, p, pmv, lane, gmask, gbase, live);\n";
+      else o << "    duo_mix_rt<G, LMASK>(S, S.mix[" << k << "], " << (int)pd.comp[pl.mix[k].lane].delay << ", C, r, H, p, pmv, lane, gmask, gbase, live);\n";
+    }
+    o << "  }\n";
+    o << "  static __device__ __forceinline__ void prefetch(const LaneRegs& r, uint32_t hnext, uint32_t cnext, int lane, uint32_t gmask, int gbase) {\n";
+    for (int k = 0; k < pl.nmix; ++k)
+      if (mix_regs) o << "    QMix" << k << "::prefetch(r, hnext, cnext, lane, gmask, gbase);\n";
+    o << "  }\n";
+    o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane, uint32_t smask) {\n"
+      << "    return " << name << "::hcomp_m(S, W, vm, env, input, lane, smask);\n  }\n};\n";
+  }
   o << "}  // namespace zpq\n\n";
+  if (duo)
+    o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << enc_kernel << "_d(const zpq::CodecParams P) {\n"
+      << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::encode_duo_body<zpq::Duo_" << name << ">(P, smem);\n}\n";
   // <enc_kernel>: time-skewed encoder when the model allows it; <enc_kernel>_l: lane-resident encoder
   // that walks bit by bit (blocks of 256 MB and more, A/B measurements)
   o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << enc_kernel << "(const zpq::CodecParams P) {\n"
@@ -358,12 +405,13 @@ int main(int argc, char** argv) {
       zpq::parse_header(wire.data(), wire.size(), h);
       const std::string id = "aot" + std::to_string(level);
       bool compiled = false;
-      std::string src = zpq::generate_model_source(h, "Model_" + id, "zpq_enc_" + id, "zpq_dec_" + id, &compiled);
+      int duo_g = 0;
+      std::string src = zpq::generate_model_source(h, "Model_" + id, "zpq_enc_" + id, "zpq_dec_" + id, &compiled, &duo_g);
       std::ostringstream reg;
       reg << "\n#include \"zpq_aot.h\"\nnamespace {\nconst unsigned char kHeader[] = {";
       for (size_t i = 0; i < wire.size(); ++i) reg << (int)wire[i] << (i + 1 < wire.size() ? "," : "");
       reg << "};\nconst zpq::AotRegistrar kReg(kHeader, sizeof kHeader, (const void*)zpq_enc_" << id << ", (const void*)zpq_enc_" << id
-          << "_l, (const void*)zpq_dec_" << id << ", \"" << id << (compiled ? " (HCOMP compiled)" : " (HCOMP interpreted)") << "\");\n}\n";
+          << "_l, " << (duo_g ? "(const void*)zpq_enc_" + id + "_d" : std::string("nullptr")) << ", " << duo_g << ", (const void*)zpq_dec_" << id << ", \"" << id << (compiled ? " (HCOMP compiled)" : " (HCOMP interpreted)") << "\");\n}\n";
       const std::string path = std::string(argv[1]) + "/zpq_gen_" + id + ".cu";
       FILE* f = fopen(path.c_str(), "w");
       if (!f) { perror(path.c_str()); return 1; }

@@ -288,6 +288,9 @@ struct LaneRegs {
   int mw[kMixRegs], mn0[kMixRegs], mn1[kMixRegs], mn2[kMixRegs];
   uint32_t moff[kMixRegs], mo0[kMixRegs], mo1[kMixRegs], mo2[kMixRegs];   // byte offsets of those weights in the table
   const uint8_t* mixtab[kMixRegs];
+  // two-role encoder: rows requested kDuoMixAhead bits ahead (mq[0] = the current bit's) and the last trained weights
+  int mq[kMixRegs][kDuoMixAhead], mt[kMixRegs][kDuoMixAhead];
+  uint32_t mqo[kMixRegs][kDuoMixAhead], mto[kMixRegs][kDuoMixAhead];
 };
 
 struct WarpCtx {

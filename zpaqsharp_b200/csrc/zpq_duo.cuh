@@ -1,0 +1,793 @@
+// zpq_duo.cuh -- two-role block encoder for sm_100a.  NVRTC-safe like zpq_devcore.cuh.
+//
+// The time-skewed encoder of zpq_pipe.cuh still runs every stage of a tick in ONE instruction stream,
+// so a tick costs the SUM of the stage latencies (ncu: 1400 cycles per bit, 18 % issue utilisation),
+// and 24 of the 32 lanes idle for an 8-component model.  This file splits the work where the data
+// dependencies allow it and packs several blocks into a warp:
+//
+//   lead role  (warp 2p)    everything that depends on the DATA only: HCOMP contexts (ZPAQL.cs:1253-1265),
+//                           hash-row look-ups and bit histories of ICM/ISSE (Predictor.cs:550-567, 375-381),
+//                           and the complete CONS / CM / ICM / MATCH components -- their predictions never
+//                           read another prediction (Predictor.cs:263-287, 365-411).
+//   coder role (warp 2p+1)  everything that depends on PREDICTIONS: ISSE weights, AVG, MIX2, SSE, MIX
+//                           (Predictor.cs:288-340, 414-455) and the arithmetic coder (Encoder.cs:87-103),
+//                           time-skewed by component delay as in zpq_pipe.cuh.
+//
+// The lead role hands one int16 per component and bit (a stretched prediction, or the bit history an
+// ISSE will index its weights with) to the coder role through a 64-bit-deep ring in shared memory,
+// plus the HCOMP contexts of the last 8 bytes; flow control is two byte counters per block.
+// Inside the coder role predictions travel between lanes by SHFL from a per-lane history of the last
+// 8 bits kept in registers, so a tick has no shared-memory read-after-write at all and its stages
+// (ISSE chain link, MIX dot product, coder) are independent instruction chains.
+//
+// A warp serves 32/G blocks at once (G = 8, 16 or 32 lanes per block, the model's component count
+// rounded up): lanes [g*G, g*G+G) of the lead warp and of the coder warp own block g of the pair.
+// Groups run in lockstep while they have work; a group that waits (ring full / ring empty / no job)
+// sits the byte out under a branch, every collective uses the group's own member mask.
+//
+// The arithmetic is exactly the reference's, per component in the same order, bit for bit; only the
+// interleaving between components and blocks changes.  Decoding cannot be split this way.
+#pragma once
+#include "zpq_pipe.cuh"
+
+namespace zpq {
+
+struct DuoSync {              // per block, in its shared slice
+  volatile uint32_t lpos;     // bytes of the current job the lead role has finished
+  volatile uint32_t qpos;     // byte the coder role is working on
+  volatile uint32_t jobseq;   // bumped by the lead role when it publishes a job
+  volatile uint32_t jobid;    // that job; 0xFFFFFFFF = the queue is empty, retire
+  volatile uint32_t cdone;    // jobseq of the last job the arithmetic coder finished
+  volatile uint32_t lstatus;  // BLK_* raised by the lead role (ZPAQL error)
+  volatile uint32_t qfin;     // bytes (ticks / 8) of the current job the coder role has finished
+  volatile uint32_t cpos;     // byte the arithmetic coder is working on
+};
+
+constexpr uint32_t kDuoRing = 64;     // bits of lead-role output kept per block
+constexpr uint32_t kDuoRetire = 0xFFFFFFFFu;
+
+// table initialisation of one role (Predictor.cs:96-165), by all 32 lanes of the calling warp
+__device__ __forceinline__ void init_block_state_role(const Plan* plan, const Tables* tab, uint8_t* arena, uint8_t* slice, int lane, int role) {
+  const int nops = plan->ninit;
+  for (int k = 0; k < nops; ++k) {
+    const InitOp op = plan->init[k];
+    if (op.role != role) continue;
+    uint8_t* dst = op.to_smem ? slice + op.dst : arena + op.dst;
+    if (op.kind == 0) {
+      const uint4 v = make_uint4(op.value, op.value, op.value, op.value);
+      uint4* q = reinterpret_cast<uint4*>(dst);
+      const uint64_t n16 = op.bytes >> 4;
+      uint64_t i = lane;
+      for (; i + 96 < n16; i += 128) { q[i] = v; q[i + 32] = v; q[i + 64] = v; q[i + 96] = v; }
+      for (; i < n16; i += 32) q[i] = v;
+    } else {
+      uint32_t* q = reinterpret_cast<uint32_t*>(dst);
+      const uint64_t nw = op.bytes >> 2;
+      if (op.kind == 1) { for (uint64_t i = lane; i < nw; i += 32) q[i] = (i & 1) ? 0u : tab->icm_init[(i >> 1) & 255]; }
+      else if (op.kind == 2) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->isse_init[i & 511]; }
+      else if (op.kind == 4) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->icm_init[i & 255]; }
+      else {
+        const uint32_t w = tab->sse_init[lane] | op.value;
+        for (uint64_t i = lane; i < nw; i += 32) q[i] = w;
+      }
+    }
+  }
+}
+
+// Lockstep policy shared by the role warps.  The groups (lanes, in the arithmetic coder warp) of a warp are only
+// cheap when they move together, and nothing else keeps them in phase, so a warp that finds some of its running
+// groups ready and others not waits a bounded number of polls for the stragglers before it serves a partial set.
+// A group that has been left behind `kLagMax` times in a row (table initialisation, a longer job) is not waited for.
+constexpr int kLagMax = 3, kSpinMax = 48;
+struct Lockstep {
+  int lag = 0, spins = 0;
+  // true: poll again (some recent straggler is not ready yet)
+  __device__ __forceinline__ bool hold(bool running, bool ready) {
+    if (__any_sync(ZPQ_FULL, running && !ready && lag < kLagMax) && spins < kSpinMax) { ++spins; return true; }
+    spins = 0;
+    lag = ready ? 0 : (running ? (lag < 255 ? lag + 1 : lag) : 0);
+    return false;
+  }
+};
+
+// sum over the G lanes of a group; every lane of the group gets the result
+template <int G>
+__device__ __forceinline__ int grp_sum(uint32_t gmask, int v) {
+  if (G == 32) return __reduce_add_sync(ZPQ_FULL, v);
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+// the last 8 predictions of a lane, newest in the low 16 bits of h0
+struct Hist {
+  uint64_t h0, h1;
+  __device__ __forceinline__ void push(int p) { h1 = (h1 << 16) | (h0 >> 48); h0 = (h0 << 16) | (uint64_t)(uint32_t)(p & 0xFFFF); }
+  __device__ __forceinline__ int at(int idx) const {   // idx 0 = newest
+    const uint64_t w = idx < 4 ? h0 : h1;
+    return (int)(int16_t)(uint16_t)(w >> ((idx & 3) * 16));
+  }
+};
+
+// ==========================================================================================
+// Lead role
+// ==========================================================================================
+template <int G>
+struct LeadCtx {
+  WarpCtx w;                 // c8, hmap4, arena, H of the block
+  DuoSync* sync;
+  int16_t* lring;            // [bit & 63][G]
+  uint32_t* hsnap;           // [byte & 7][G]
+  const uint8_t* in; const uint8_t* preamble;
+  uint32_t pre_len, total, s, seq, status;
+  uint32_t cb0, cb1, cb2, hnext;
+  int st;                    // 0 idle, 1 running, 2 all bytes done (waiting for the coder role), 3 retired
+  __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+    if (i < pre_len) return preamble[i];
+    return i < total ? in[i - pre_len] : 0u;
+  }
+};
+
+// End of a byte in a MATCH component (Predictor.cs:382-411).  The index slot was loaded when the byte began
+// (r.t0); the backward verify compares 8 byte pairs per round trip instead of one.
+__device__ __forceinline__ void duo_match_byte(const WarpCtx& W, LaneRegs& r, int y) {
+  uint8_t* buf = r.tab2;
+  buf[r.mpos] = (uint8_t)(W.c8 * 2 + y);
+  r.mpos = (r.mpos + 1) & r.mask2;
+  uint32_t* idx = reinterpret_cast<uint32_t*>(r.tab) + (r.h & r.mask);
+  if (r.ma == 0) {
+    r.mb = r.mpos - (uint32_t)r.t0;
+    if (r.mb & r.mask2) {
+      while (r.ma < 255) {
+        uint32_t a[8], b[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a[k] = buf[(r.mpos - r.ma - 1 - k) & r.mask2];
+          b[k] = buf[(r.mpos - r.ma - r.mb - 1 - k) & r.mask2];
+        }
+        uint32_t n = 0;
+        bool go = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { go = go && a[k] == b[k] && r.ma + n < 255; n += go ? 1u : 0u; }
+        r.ma += n;
+        if (n < 8) break;
+      }
+    }
+  } else r.ma += r.ma < 255;
+  *idx = r.mpos;
+  if (r.ma) r.mbyte = buf[(r.mpos - r.mb) & r.mask2];
+}
+
+// One bit of the lead role for the lane's component.  K = bit of the byte (0 = most significant).
+template <class DM, int K>
+__device__ __forceinline__ void duo_lead_tick(const Shared& S, LeadCtx<DM::G>& C, LaneRegs& r, FindAhead& F, uint8_t*& row2,
+                                               VM& vm, VMEnv& env, int gl, uint32_t gmask, int gbase) {
+  constexpr int G = DM::G;
+  const bool hashed = (r.type == C_ICM || r.type == C_ISSE);
+  const uint32_t s = C.s;
+  if (K == 0) {
+    // ---- byte s begins: contexts were written when byte s-1 began ----
+    C.cb2 = C.fetch(s + 2);
+    r.h = C.hsnap[(s & 7) * G + gl];
+    C.w.c8 = 1; C.w.hmap4 = 1;
+    if (hashed) {
+      if (s == 0) lane_find(r, r.h + 16);
+      else find_swap(r, F, row2, r.h + 16);
+      find_issue(r, r.h + 16u * (16u + (C.cb0 >> 4)), F);      // second nibble of this byte
+    }
+    // contexts of byte s+1 (HCOMP sees byte s, ZPAQL.cs:1253-1265) and the lines that byte will touch
+    if (DM::hcomp(S, C.w, vm, env, C.cb0, gl, gmask)) C.status = BLK_ZPAQL;
+    const uint32_t hn = C.w.H[gl & C.w.hmask];
+    C.hsnap[((s + 1) & 7) * G + gl] = hn;
+    C.hnext = hn;
+    if (hashed) {
+      prefetch_l2(r.tab + (((hn + 16u) * 16u) & r.mask));
+      prefetch_l2(r.tab + (((hn + 16u * (16u + (C.cb1 >> 4))) * 16u) & r.mask));
+    }
+    if (r.type == C_MATCH) prefetch_l2(reinterpret_cast<const uint32_t*>(r.tab) + (hn & r.mask));
+    DM::prefetch(r, hn, C.cb1, gl, gmask, gbase);
+  }
+  const int y = (int)((C.cb0 >> (7 - K)) & 1);
+  int val = 0;
+  if (DM::HAS_HASHED) {
+    // bit history of the slot this bit selects; ICM also predicts and learns here (Predictor.cs:267-272, 375-381).
+    // Straight-line on all lanes: lanes of other types read harmless dummies and store nothing.
+    const bool icm = r.type == C_ICM;
+    const uint32_t si = (uint32_t)C.w.hmap4 & 15u;
+    const uint32_t bh = r.row[si];
+    const uint32_t pn = r.cm[icm ? bh : 0u];
+    const uint32_t nx = S.ns[bh * 4 + y];
+    const int sp = S.stretch[(pn >> 8) & 32767u];
+    if (hashed) r.row[si] = (uint8_t)nx;
+    if (icm) r.cm[bh] = pn + (uint32_t)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
+    val = icm ? sp : (int)bh;
+  }
+  if (DM::HAS_MATCH) {                                          // Predictor.cs:273-287, 382-411
+    const bool mat = r.type == C_MATCH;
+    if (K == 0 && mat) r.t0 = (int)reinterpret_cast<const uint32_t*>(r.tab)[r.h & r.mask];   // index slot of this byte's context, used at K == 7
+    const uint32_t bit = (r.mbyte >> (7 - K)) & 1;
+    const int pm = S.stretch[(S.dt2k[r.ma & 255u] * (1 - 2 * (int)bit)) & 32767];
+    val = mat ? (r.ma ? pm : 0) : val;
+    if (mat && (int)bit != y) r.ma = 0;
+    if (K == 7 && mat) duo_match_byte(C.w, r, y);
+  }
+  if (DM::HAS_CM) {
+    if (r.type == C_CM) {                                      // Predictor.cs:263-266, 365-373
+      pa_cm(S, C.w, r);
+      val = r.p;
+      up_cm(S, r, y);
+    }
+  }
+  if (DM::HAS_CONS) {
+    if (r.type == C_CONS) val = ((int)r.a1 - 128) * 4;         // Predictor.cs:96-98
+  }
+  C.lring[((s * 8u + K) & (kDuoRing - 1)) * G + gl] = (int16_t)val;
+  // ---- shift the bit into c8 / hmap4 (Predictor.cs:463-474) ----
+  const int c8 = C.w.c8 * 2 + y;
+  if (K == 7) {
+    C.cb0 = C.cb1; C.cb1 = C.cb2;
+  } else if (K == 3) {
+    C.w.hmap4 = (C.w.hmap4 & 0xf) << 5 | y << 4 | 1;
+    if (hashed) {
+      find_resolve(F, row2);                                   // requested when the byte began
+      find_swap(r, F, row2, r.h + 16u * (uint32_t)c8);
+      find_issue(r, C.hnext + 16u, F);                         // first nibble of the next byte
+    }
+  } else {
+    C.w.hmap4 = (C.w.hmap4 & 0x1f0) | (((C.w.hmap4 & 0xf) * 2 + y) & 0xf);
+  }
+  if (K == 7 && hashed) find_resolve(F, row2);                 // requested at bit 3; swapped in when the next byte begins
+  C.w.c8 = c8;
+}
+
+template <class DM>
+__device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* smem, const Shared& S, int pair) {
+  constexpr int G = DM::G, B = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G, gbase = lane & ~(G - 1);
+  const uint32_t gmask = G == 32 ? ZPQ_FULL : (((1u << (G & 31)) - 1u) << gbase);
+  const Plan* plan = P.plan;
+  const uint32_t b = (uint32_t)pair * B + grp;
+  const bool valid = b < P.wb && blockIdx.x * P.wb + b < P.resident;
+  // groups without a block alias block 0 of the CTA for their (never used) pointers
+  const uint32_t bb = valid ? b : 0u;
+  Blk w;
+  bind_block(P, smem, w, blockIdx.x * P.wb + bb, (int)bb);
+  LaneRegs r;
+  lane_load(S, P, w, r, gl < S.n ? gl : 0);
+  if (gl >= S.n) r.type = C_NONE;
+  r.row = w.slice + plan->smem_rows + gl * 16;
+  uint8_t* row2 = r.row + 16 * G;
+  // maps live in the shared slice (the host launches this kernel only then): keep the pointer provably shared
+  r.cm = r.type == C_ICM ? reinterpret_cast<uint32_t*>(w.slice + S.comp[gl < S.n ? gl : 0].smem_cm)
+                         : reinterpret_cast<uint32_t*>(const_cast<int16_t*>(S.stretch));
+  LeadCtx<G> C;
+  C.sync = reinterpret_cast<DuoSync*>(w.slice + plan->smem_sync);
+  C.lring = reinterpret_cast<int16_t*>(w.slice + plan->smem_pring);
+  C.hsnap = reinterpret_cast<uint32_t*>(w.slice + plan->smem_hsnap);
+  C.preamble = P.preamble;
+  C.in = P.in; C.pre_len = 0; C.total = 0; C.s = 0; C.seq = 0; C.status = BLK_OK;
+  C.cb0 = C.cb1 = C.cb2 = 0; C.hnext = 0;
+  C.st = valid ? 0 : 3;
+  C.w.arena = w.arena; C.w.H = w.H; C.w.hmask = w.hmask; C.w.c8 = 1; C.w.hmap4 = 1;
+  VM vm; VMEnv env;
+  vm.b = vm.c = vm.d = vm.f = 0;
+  env.code = S.hcomp; env.len = S.hcomp_len;
+  env.H = w.H; env.hmask = w.hmask; env.M = w.M; env.mmask = w.mmask; env.R = w.R;
+  env.out = nullptr; env.out_pos = 0; env.out_cap = 0;
+  FindAhead F;
+  F.r0 = F.r1 = F.r2 = make_uint4(0, 0, 0, 0); F.h0 = F.chk = F.at = 0; F.hz = true;
+  if (valid && gl == 0) { C.sync->lpos = 0; C.sync->qpos = 0; C.sync->jobid = 0; C.sync->cdone = 0; C.sync->lstatus = 0; C.sync->jobseq = 0; C.sync->qfin = 0; C.sync->cpos = 0; }
+  __syncthreads();   // the coder role reads the sync words from here on
+
+  constexpr uint32_t DB = ((uint32_t)DM::D + 7u) / 8u;   // bytes the coder role reads back behind its own byte
+  Lockstep LS;
+  for (;;) {
+    // ---- job management (warp-convergent) ----
+    if (C.st == 2 && C.sync->cdone == C.seq) C.st = 0;
+    uint32_t want = __ballot_sync(ZPQ_FULL, C.st == 0 && gl == 0);
+    while (want) {
+      const int src = __ffs(want) - 1;
+      want &= want - 1;
+      uint32_t job = 0;
+      if (lane == src) job = atomicAdd(P.queue, 1u);
+      job = __shfl_sync(ZPQ_FULL, job, src);
+      const bool mine = gbase == src;
+      if (job >= P.njobs) {
+        if (mine) {
+          C.st = 3;
+          if (gl == 0) { C.sync->jobid = kDuoRetire; __threadfence_block(); C.sync->jobseq = C.seq + 1; }
+        }
+        continue;
+      }
+      const EncJob J = P.ejobs[job];
+      uint8_t* arena_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.arena, src));
+      uint8_t* slice_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.slice, src));
+      if (J.in_len != 0xFFFFFFFFu) init_block_state_role(plan, P.tab, arena_g, slice_g, lane, 0);   // Predictor.init + ZPAQL.inith
+      __syncwarp();
+      if (mine) {
+        C.in = P.in + J.in_off; C.pre_len = J.pre_len;
+        C.total = J.in_len == 0xFFFFFFFFu ? 0u : J.pre_len + J.in_len;
+        C.s = 0; C.status = BLK_OK; C.seq += 1;
+        r.cxt = r.c = r.ma = r.mb = r.mpos = r.h = 0; r.t0 = r.t1 = 0; r.p = 0; r.mbyte = 0; r.mbit = 0;
+        if (r.type == C_MATCH) r.tab2[0] = 1;                  // Predictor.cs:118
+        C.w.c8 = 1; C.w.hmap4 = 1;
+        vm.b = vm.c = vm.d = vm.f = 0;
+        F.hz = true;
+        if (gl < G) C.hsnap[gl] = 0;                           // contexts of byte 0 are H == 0
+        C.cb0 = C.fetch(0); C.cb1 = C.fetch(1); C.cb2 = 0;
+        C.st = C.total ? 1 : 2;
+      }
+      __syncwarp();
+      if (mine && gl == 0) {
+        C.sync->lpos = 0; C.sync->qpos = 0; C.sync->qfin = 0; C.sync->cpos = 0; C.sync->lstatus = 0; C.sync->jobid = job;
+        __threadfence_block();
+        C.sync->jobseq = C.seq;
+      }
+    }
+    // ---- flow control: stay at most 6 - DB bytes ahead of the coder role ----
+    const bool run = C.st == 1 && C.s + DB <= C.sync->qpos + 6u;
+    if (!__any_sync(ZPQ_FULL, run)) {
+      if (__all_sync(ZPQ_FULL, C.st == 3)) break;
+      __nanosleep(200);
+      continue;
+    }
+    if (LS.hold(C.st == 1, run)) continue;
+    if (run) {
+      duo_lead_tick<DM, 0>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      duo_lead_tick<DM, 1>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      duo_lead_tick<DM, 2>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      duo_lead_tick<DM, 3>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      duo_lead_tick<DM, 4>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      duo_lead_tick<DM, 5>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      duo_lead_tick<DM, 6>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      duo_lead_tick<DM, 7>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      ++C.s;
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (run) {
+      if (gl == 0) { if (C.status) C.sync->lstatus = C.status; C.sync->lpos = C.s; }
+      if (C.s == C.total) C.st = 2;
+    }
+  }
+}
+
+// ==========================================================================================
+// Coder role
+// ==========================================================================================
+template <int G>
+struct CoderCtx {
+  DuoSync* sync;
+  const int16_t* lring;
+  const uint32_t* hsnap;
+  int16_t* pfring;           // [bit & 63] stretched prediction of the last component, for the arithmetic coder warp
+  uint8_t* arena;
+  const uint8_t* in; const uint8_t* preamble;
+  uint32_t pre_len, total, s, seq, job;
+  uint32_t T, NB, bits;      // tick == bit time of the lead stage; bit k of `bits` = y(T-k)
+  uint32_t cb0, cb1, cb2;
+  int st;                    // 0 idle, 1 running, 3 retired
+  __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+    const uint8_t* q = i < pre_len ? preamble + i : in + (i - pre_len);
+    return i < total ? (uint32_t)*q : 0u;
+  }
+  // partial byte (leading 1 + the bits already coded) of bit t as a stage d bits behind the lead sees it
+  __device__ __forceinline__ uint32_t c8(uint32_t t, uint32_t d) const {
+    const uint32_t k = t & 7;
+    return ((bits >> (d + 1)) & ((1u << k) - 1)) | (1u << k);
+  }
+};
+
+// per-lane constants of the coder role
+struct CoderLane {
+  int jL, kL;        // 1: input j / k is a lead-role component (read from the ring)
+  int dj, dk;        // else: index into the producer's history (0 = its previous tick)
+};
+
+// MIX K evaluated by the group DM_ bits behind the lead (Predictor.cs:302-316, 427-439); see MixPipe.
+// LMASK: bit i set = component i is a lead-role component.
+template <int G, int K, int MIXLANE, int J0, int M, int RATE, unsigned MASK, unsigned CMASK, int DM_, unsigned LMASK>
+struct MixDuo {
+  static __device__ __forceinline__ uint32_t rowoff(const CoderCtx<G>& C, uint32_t t, uint32_t d, int gl) {
+    const uint32_t h = C.hsnap[((t >> 3) & 7) * G + MIXLANE];
+    return ((h + (C.c8(t, d) & CMASK)) & MASK) * (uint32_t)(M * 4) + (uint32_t)gl * 4u;
+  }
+  // FAST: every group of the warp is inside its block with all stages (no range tests, whole-warp collectives);
+  // `live` = this group really owns a running block (false: it rides along and must not store).
+  // KT = bit of the byte the LEAD stage is at (the tick index inside the byte).
+  template <bool FAST, int KT>
+  static __device__ __forceinline__ void tick(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, const Hist& H, int& p, int& pmv, int gl,
+                                               uint32_t gmask, int gbase, bool live) {
+    constexpr int A = kDuoMixAhead;
+    const uint32_t tm = C.T - (uint32_t)DM_, t2 = tm + A;
+    const bool on2 = FAST || t2 < C.NB, onm = FAST || tm < C.NB;
+    const uint32_t o2 = on2 ? rowoff(C, t2, (uint32_t)(DM_ - A), gl) : 0xFFFFFFFFu;
+    int n2 = 0;
+    if (on2 && gl < M) n2 = *reinterpret_cast<const int*>(r.mixtab[K] + o2);
+    // input j0+gl of bit tm: from the ring (lead-role component) or from its lane's history
+    int hv = H.at((DM_ - r.d - 1) & 7);
+    if (J0) hv = __shfl_sync(gmask, hv, gbase + ((J0 + gl) & (G - 1)));
+    const int lv = C.lring[(tm & (kDuoRing - 1)) * G + ((J0 + gl) & (G - 1))];
+    const int pin = gl < M ? (((LMASK >> ((J0 + gl) & 31)) & 1u) ? lv : hv) : 0;
+    // The row of bit tm was requested A ticks ago; a training of the last A bits that hit the same row has to be
+    // forwarded (mt[j] = weight trained at bit tm-1-j).  With the whole partial byte in the row index
+    // (CMASK == 255, >= 256 rows) rows of one byte are pairwise distinct, so only trainings of the PREVIOUS
+    // byte can match: bit kBit of a byte checks j >= kBit only, and bits >= A of a byte check nothing.
+    constexpr bool kDistinct = CMASK == 255u && MASK >= 255u;
+    constexpr int kBit = (KT - DM_) & 7;
+    int wcur = r.mq[K][0];
+#pragma unroll
+    for (int j = A - 1; j >= 0; --j)
+      if (!(kDistinct && j < kBit)) wcur = r.mto[K][j] == r.mqo[K][0] ? r.mt[K][j] : wcur;
+    const int acc = grp_sum<G>(gmask, (wcur >> 8) * pin);
+    const int pm = clamp2k(acc >> 8);
+    const int y = (int)((C.bits >> DM_) & 1);
+    const int err = ((y * 32767 - (int)S.squash[pm + 2048]) * RATE) >> 4;
+    const int wn = clamp512k(wcur + ((err * pin + (1 << 12)) >> 13));
+    if (onm && live && gl < M) *reinterpret_cast<int*>(const_cast<uint8_t*>(r.mixtab[K]) + r.mqo[K][0]) = wn;
+    if (onm) {
+#pragma unroll
+      for (int j = A - 1; j > 0; --j) { r.mt[K][j] = r.mt[K][j - 1]; r.mto[K][j] = r.mto[K][j - 1]; }
+      r.mt[K][0] = wn; r.mto[K][0] = r.mqo[K][0];
+    }
+#pragma unroll
+    for (int j = 0; j < A - 1; ++j) { r.mq[K][j] = r.mq[K][j + 1]; r.mqo[K][j] = r.mqo[K][j + 1]; }
+    r.mq[K][A - 1] = n2; r.mqo[K][A - 1] = o2;
+    if (gl == MIXLANE) p = pm;
+    pmv = pm;
+  }
+  // lead role, start of byte s: pull the 8 rows byte s+1 will use into L2 (lane k: row of bit k)
+  static __device__ __forceinline__ void prefetch(const LaneRegs& r, uint32_t hnext, uint32_t cnext, int gl, uint32_t gmask, int gbase) {
+    const uint32_t h = __shfl_sync(gmask, hnext, gbase + MIXLANE);
+    if (gl < 8) {
+      const uint32_t c8 = (1u << gl) | (cnext >> (8 - gl));
+      const uint8_t* row = r.mixtab[K] + ((h + (c8 & CMASK)) & MASK) * (uint32_t)(M * 4);
+      prefetch_l2(row);
+      if ((M * 4) & (M * 4 - 1)) prefetch_l2(row + M * 4 - 4);
+    }
+  }
+};
+
+// MIX described at run time (more than kMixRegs mixers): weights read and written in place.
+template <int G, unsigned LMASK>
+__device__ __forceinline__ void duo_mix_rt(const Shared& S, const MixDesc& md, int dm, const CoderCtx<G>& C, LaneRegs& r, const Hist& H,
+                                            int& p, int& pmv, int gl, uint32_t gmask, int gbase, bool live) {
+  const uint32_t tm = C.T - (uint32_t)dm;
+  const uint32_t h = C.hsnap[((tm >> 3) & 7) * G + md.lane];
+  const uint32_t rowi = ((h + (C.c8(tm, (uint32_t)dm) & md.cmask)) & md.mask) * md.m;
+  int* wp = reinterpret_cast<int*>(C.arena + md.tab) + rowi + gl;
+  int hv = H.at((dm - r.d - 1) & 7);
+  hv = __shfl_sync(gmask, hv, gbase + ((md.j0 + gl) & (G - 1)));
+  const int lv = C.lring[(tm & (kDuoRing - 1)) * G + ((md.j0 + gl) & (G - 1))];
+  const bool on = live && tm < C.NB && gl < md.m;
+  const int pin = gl < md.m ? (((LMASK >> ((md.j0 + gl) & 31)) & 1u) ? lv : hv) : 0;
+  const int wv = on ? *wp : 0;
+  const int pm = clamp2k(grp_sum<G>(gmask, (wv >> 8) * pin) >> 8);
+  const int y = (int)((C.bits >> dm) & 1);
+  const int err = ((y * 32767 - (int)S.squash[pm + 2048]) * (int)md.rate) >> 4;
+  if (on) *wp = clamp512k(wv + ((err * pin + (1 << 12)) >> 13));
+  if (gl == md.lane) p = pm;
+  pmv = pm;
+}
+
+// One bit of the coder role.  DM (generated by zpq_codegen.cpp) supplies the constants
+//   G, N, D, LDEPTH, HDEPTH, LMASK, FINAL_MIX, HAS_*, NEEDK and
+//   DM::lanes(S, C, r, pj, pk, y, act, t, p, gl)                       AVG / MIX2 / SSE lanes
+//   DM::mixes<FAST, K>(S, C, r, H, p, pmv, gl, gmask, gbase, live)      every MIX
+// FAST: steady state of every group of the warp -- no range tests, whole-warp collectives, and the tick is one
+// basic block, so consecutive ISSE chain links and the MIX overlap.
+template <class DM, int K, bool FAST>
+__device__ __forceinline__ void duo_coder_tick(const Shared& S, CoderCtx<DM::G>& C, LaneRegs& r, const CoderLane& L, Hist& H, int gl,
+                                                uint32_t gmask_rt, int gbase, bool live) {
+  constexpr int G = DM::G;
+  constexpr uint32_t D = (uint32_t)DM::D;
+  const uint32_t gmask = FAST ? ZPQ_FULL : gmask_rt;
+  if (K == 0) C.cb2 = C.fetch(C.s + 2);
+  C.bits = C.bits << 1 | ((C.cb0 >> (7 - K)) & 1u);
+  const uint32_t t = C.T - (uint32_t)r.d;
+  const bool act = live && gl < DM::N && (FAST || t < C.NB);
+  const uint32_t slot = (t & (kDuoRing - 1)) * G;
+  const int y = (int)((C.bits >> r.d) & 1);
+  // ---- inputs of lane-owned components: ring (lead-role producer) or the producer lane's history ----
+  int pj, pk = 0;
+  {
+    const int lj = C.lring[slot + r.srcj];
+    int hj;
+    if (DM::LDEPTH <= 1) hj = (int)(int16_t)(uint16_t)__shfl_sync(gmask, (uint32_t)H.h0, gbase + r.srcj);
+    else {
+      const uint64_t a0 = __shfl_sync(gmask, (unsigned long long)H.h0, gbase + r.srcj);
+      const uint64_t a1 = DM::LDEPTH > 4 ? __shfl_sync(gmask, (unsigned long long)H.h1, gbase + r.srcj) : 0ull;
+      hj = (int)(int16_t)(uint16_t)((L.dj < 4 ? a0 : a1) >> ((L.dj & 3) * 16));
+    }
+    pj = L.jL ? lj : hj;
+    if (DM::NEEDK) {
+      const int lk = C.lring[slot + r.srck];
+      int hk;
+      if (DM::LDEPTH <= 1) hk = (int)(int16_t)(uint16_t)__shfl_sync(gmask, (uint32_t)H.h0, gbase + r.srck);
+      else {
+        const uint64_t a0 = __shfl_sync(gmask, (unsigned long long)H.h0, gbase + r.srck);
+        const uint64_t a1 = DM::LDEPTH > 4 ? __shfl_sync(gmask, (unsigned long long)H.h1, gbase + r.srck) : 0ull;
+        hk = (int)(int16_t)(uint16_t)((L.dk < 4 ? a0 : a1) >> ((L.dk & 3) * 16));
+      }
+      pk = L.kL ? lk : hk;
+    }
+  }
+  const int lown = C.lring[slot + gl];
+  int p = ((DM::LMASK >> gl) & 1u) ? lown : 0;    // a lead-role component's prediction is its ring entry
+  if (DM::HAS_ISSE) {
+    // ---- ISSE, branch-free on all lanes (Predictor.cs:317-326, 440-449; the bit history was advanced by the lead role) ----
+    const bool isse = r.type == C_ISSE;
+    const uint32_t bh = (uint32_t)lown & 255u;
+    const int2 wt = *reinterpret_cast<const int2*>(r.cm + bh * 2);
+    const int pe = clamp2k((wt.x * pj + wt.y * 64) >> 16);
+    const int err = y * 32767 - (int)S.squash[pe + 2048];
+    int2 nw;
+    nw.x = clamp512k(wt.x + ((err * pj + (1 << 12)) >> 13));
+    nw.y = clamp512k(wt.y + ((err + 16) >> 5));
+    if (act && isse) *reinterpret_cast<int2*>(r.cm + bh * 2) = nw;
+    p = isse ? pe : p;
+  }
+  DM::lanes(S, C, r, pj, pk, y, act, t, p, gl);
+  int pmv = 0;
+  DM::template mixes<FAST, K>(S, C, r, H, p, pmv, gl, gmask, gbase, live);
+  H.push(p);
+  // the last component's prediction of bit t goes to the arithmetic coder warp
+  if (gl == DM::N - 1 && act) C.pfring[t & (kDuoRing - 1)] = (int16_t)p;
+  if (K == 7) { C.cb0 = C.cb1; C.cb1 = C.cb2; }
+  ++C.T;
+}
+
+// lane-owned components other than ISSE, at bit t (see pipe_avg / pipe_mix2 / pipe_sse)
+template <int G>
+__device__ __forceinline__ void duo_avg(LaneRegs& r, int pj, int pk, bool act, int& p) {   // Predictor.cs:288-290
+  if (act) p = ev_avg(r, pj, pk);
+}
+template <int G>
+__device__ __forceinline__ void duo_mix2(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, int pj, int pk, int y, bool act, uint32_t t,
+                                          int& p, int gl) {   // Predictor.cs:291-301, 414-426
+  if (!act) return;
+  const uint32_t h = C.hsnap[((t >> 3) & 7) * G + gl];
+  r.cxt = (h + (C.c8(t, (uint32_t)r.d) & r.a5)) & r.mask;
+  r.t0 = reinterpret_cast<const uint16_t*>(r.tab)[r.cxt];
+  r.p = ev_mix2(r, pj, pk);
+  p = r.p;
+  up_mix2(S, r, y, pj, pk);
+}
+template <int G>
+__device__ __forceinline__ void duo_sse(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, int pj, int y, bool act, uint32_t t, int& p,
+                                         int gl) {   // Predictor.cs:327-340, 451-455
+  if (!act) return;
+  const uint32_t h = C.hsnap[((t >> 3) & 7) * G + gl];
+  r.t0 = (int)((h + C.c8(t, (uint32_t)r.d)) * 32);
+  r.p = ev_sse(S, r, pj);
+  p = r.p;
+  up_sse(S, r, y);
+}
+
+template <class DM>
+__device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* smem, const Shared& S, int pair) {
+  constexpr int G = DM::G, B = 32 / G;
+  constexpr uint32_t D = (uint32_t)DM::D;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G, gbase = lane & ~(G - 1);
+  const uint32_t gmask = G == 32 ? ZPQ_FULL : (((1u << (G & 31)) - 1u) << gbase);
+  const Plan* plan = P.plan;
+  const uint32_t b = (uint32_t)pair * B + grp;
+  const bool valid = b < P.wb && blockIdx.x * P.wb + b < P.resident;
+  const uint32_t bb = valid ? b : 0u;
+  Blk w;
+  bind_block(P, smem, w, blockIdx.x * P.wb + bb, (int)bb);
+  LaneRegs r;
+  lane_load(S, P, w, r, gl < S.n ? gl : 0);
+  if (gl >= S.n) { r.type = C_NONE; r.d = 0; r.srcj = r.srck = 0; }
+  // maps live in the shared slice (the host launches this kernel only then): keep the pointer provably shared
+  r.cm = r.type == C_ISSE ? reinterpret_cast<uint32_t*>(w.slice + S.comp[gl < S.n ? gl : 0].smem_cm)
+                          : reinterpret_cast<uint32_t*>(const_cast<int16_t*>(S.stretch));
+  CoderLane L;
+  {
+    const int tj = S.comp[r.srcj].type, tk = S.comp[r.srck].type;
+    L.jL = (tj == C_CONS || tj == C_CM || tj == C_ICM || tj == C_MATCH) ? 1 : 0;
+    L.kL = (tk == C_CONS || tk == C_CM || tk == C_ICM || tk == C_MATCH) ? 1 : 0;
+    L.dj = (r.d - (int)S.comp[r.srcj].delay - 1) & 7;
+    L.dk = (r.d - (int)S.comp[r.srck].delay - 1) & 7;
+  }
+  CoderCtx<G> C;
+  C.sync = reinterpret_cast<DuoSync*>(w.slice + plan->smem_sync);
+  C.lring = reinterpret_cast<const int16_t*>(w.slice + plan->smem_pring);
+  C.hsnap = reinterpret_cast<const uint32_t*>(w.slice + plan->smem_hsnap);
+  C.pfring = reinterpret_cast<int16_t*>(w.slice + plan->smem_pfring);
+  C.arena = w.arena;
+  C.preamble = P.preamble; C.in = P.in;
+  C.pre_len = 0; C.total = 0; C.s = 0; C.seq = 0; C.job = 0;
+  C.T = 0; C.NB = 0; C.bits = 0; C.cb0 = C.cb1 = C.cb2 = 0;
+  C.st = valid ? 0 : 3;
+  Hist H; H.h0 = H.h1 = 0;
+  Lockstep LS;
+  __syncthreads();   // pairs with the lead role: sync words are initialised
+
+  for (;;) {
+    // ---- job management (warp-convergent) ----
+    bool fresh = false;
+    if (C.st == 0 && C.sync->jobseq != C.seq) {
+      __threadfence_block();
+      C.seq += 1;
+      C.job = C.sync->jobid;
+      if (C.job == kDuoRetire) C.st = 3; else fresh = true;
+    }
+    uint32_t want = __ballot_sync(ZPQ_FULL, fresh && gl == 0);
+    while (want) {
+      const int src = __ffs(want) - 1;
+      want &= want - 1;
+      const uint32_t job = __shfl_sync(ZPQ_FULL, C.job, src);
+      const EncJob J = P.ejobs[job];
+      const bool mine = gbase == src;
+      if (J.in_len == 0xFFFFFFFFu) continue;     // the pre-processing stage overflowed its slot: the coder warp reports it
+      uint8_t* arena_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.arena, src));
+      uint8_t* slice_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.slice, src));
+      init_block_state_role(plan, P.tab, arena_g, slice_g, lane, 1);
+      __syncwarp();
+      if (mine) {
+        C.in = P.in + J.in_off;
+        C.pre_len = J.pre_len; C.total = J.pre_len + J.in_len;
+        C.s = 0; C.T = 0; C.NB = C.total * 8u; C.bits = 0;
+        H.h0 = H.h1 = 0;
+        r.cxt = 0; r.t0 = r.t1 = 0; r.p = 0;
+        for (int k = 0; k < kMixRegs; ++k)
+          for (int j = 0; j < kDuoMixAhead; ++j) { r.mq[k][j] = r.mt[k][j] = 0; r.mqo[k][j] = 0xFFFFFFFFu; r.mto[k][j] = 0xFFFFFFFEu; }
+        C.cb0 = C.fetch(0); C.cb1 = C.fetch(1); C.cb2 = 0;
+        C.st = 1;
+      }
+    }
+    // ---- flow control: byte s needs the lead role's byte s (none while the pipeline drains), and the arithmetic
+    //      coder must be done with the ring slots this byte overwrites ----
+    bool run = false;
+    if (C.st == 1) {
+      const uint32_t need = C.s + 1 < C.total ? C.s + 1 : C.total;
+      run = C.sync->lpos >= need && C.s <= C.sync->cpos + 6u;
+    }
+    if (!__any_sync(ZPQ_FULL, run)) {
+      if (__all_sync(ZPQ_FULL, C.st == 3)) break;
+      __nanosleep(100);
+      continue;
+    }
+    if (LS.hold(C.st == 1, run)) continue;
+    // fast path: every group that owns a running block is ready and in its steady state (all stages inside
+    // the block for the whole byte); groups without a running block ride along with their stores switched off
+    constexpr uint32_t PRO = (D + 7u) / 8u;
+    const bool live = C.st == 1;
+    const bool steady = run && C.s >= PRO && C.s + 1 < C.total;
+    if (run) { __threadfence_block(); if (gl == 0) C.sync->qpos = C.s; }
+    __syncwarp();   // the lanes must be CONVERGED when they enter the fast path: its shuffles are whole-warp
+    const bool fast = __all_sync(ZPQ_FULL, steady || !live);
+    if (fast) {
+      duo_coder_tick<DM, 0, true>(S, C, r, L, H, gl, gmask, gbase, live);
+      duo_coder_tick<DM, 1, true>(S, C, r, L, H, gl, gmask, gbase, live);
+      duo_coder_tick<DM, 2, true>(S, C, r, L, H, gl, gmask, gbase, live);
+      duo_coder_tick<DM, 3, true>(S, C, r, L, H, gl, gmask, gbase, live);
+      duo_coder_tick<DM, 4, true>(S, C, r, L, H, gl, gmask, gbase, live);
+      duo_coder_tick<DM, 5, true>(S, C, r, L, H, gl, gmask, gbase, live);
+      duo_coder_tick<DM, 6, true>(S, C, r, L, H, gl, gmask, gbase, live);
+      duo_coder_tick<DM, 7, true>(S, C, r, L, H, gl, gmask, gbase, live);
+    } else if (run) {
+      duo_coder_tick<DM, 0, false>(S, C, r, L, H, gl, gmask, gbase, true);
+      duo_coder_tick<DM, 1, false>(S, C, r, L, H, gl, gmask, gbase, true);
+      duo_coder_tick<DM, 2, false>(S, C, r, L, H, gl, gmask, gbase, true);
+      duo_coder_tick<DM, 3, false>(S, C, r, L, H, gl, gmask, gbase, true);
+      duo_coder_tick<DM, 4, false>(S, C, r, L, H, gl, gmask, gbase, true);
+      duo_coder_tick<DM, 5, false>(S, C, r, L, H, gl, gmask, gbase, true);
+      duo_coder_tick<DM, 6, false>(S, C, r, L, H, gl, gmask, gbase, true);
+      duo_coder_tick<DM, 7, false>(S, C, r, L, H, gl, gmask, gbase, true);
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (run) {
+      ++C.s;
+      if (gl == 0) C.sync->qfin = C.s;
+      if (C.T >= C.NB + D) C.st = 0;     // every prediction of the block is in the ring
+    }
+  }
+}
+
+// ==========================================================================================
+// Arithmetic coder warp (Encoder.cs:39-103): ONE warp per CTA, lane b codes block b of the CTA.  The coder is
+// scalar per block and full of data-dependent branches (renormalisation, byte output), so it is kept out of
+// the prediction warps: it reads the final stretched prediction of every bit from the block's ring.
+// ==========================================================================================
+template <class DM>
+__device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* smem, const Shared& S) {
+  constexpr uint32_t D = (uint32_t)DM::D;
+  constexpr uint32_t CD = (D + 7u + 7u) / 8u;     // byte c is complete in the ring once the coder role has finished c + CD bytes
+  const int lane = threadIdx.x & 31;
+  const Plan* plan = P.plan;
+  const uint32_t b = (uint32_t)lane;
+  const bool valid = b < P.wb && blockIdx.x * P.wb + b < P.resident;
+  uint8_t* slice = smem + P.sm.slices + (valid ? b : 0u) * P.sm.slice_bytes;
+  DuoSync* sync = reinterpret_cast<DuoSync*>(slice + plan->smem_sync);
+  const int16_t* pfring = reinterpret_cast<const int16_t*>(slice + plan->smem_pfring);
+  int st = valid ? 0 : 3;
+  Lockstep LS;
+  uint32_t seq = 0, job = 0, c = 0, total = 0, pre_len = 0, cb = 0, cbn = 0, low = 1, high = 0xFFFFFFFFu;
+  const uint8_t* in = P.in; uint8_t* out = P.out;
+  uint64_t out_cap = 0, opos = 0;
+  auto fetch = [&](uint32_t i) -> uint32_t {
+    const uint8_t* q = i < pre_len ? P.preamble + i : in + (i - pre_len);
+    return i < total ? (uint32_t)*q : 0u;
+  };
+  auto normalise = [&]() {                                       // Encoder.cs:95-102
+    while ((high ^ low) < 0x1000000u) {
+      if (opos < out_cap) out[opos] = (uint8_t)(high >> 24);
+      ++opos;
+      high = high << 8 | 255; low <<= 8; low += (low == 0);
+    }
+  };
+  __syncthreads();   // pairs with the lead role: sync words are initialised
+
+  for (;;) {
+    if (st == 0 && sync->jobseq != seq) {
+      __threadfence_block();
+      seq += 1;
+      job = sync->jobid;
+      if (job == kDuoRetire) st = 3;
+      else {
+        const EncJob J = P.ejobs[job];
+        if (J.in_len == 0xFFFFFFFFu) {     // the pre-processing stage overflowed its slot
+          P.results[job].out_len = 0; P.results[job].status = BLK_OVERFLOW;
+          __threadfence_block();
+          sync->cdone = seq;
+        } else {
+          in = P.in + J.in_off; out = P.out + J.out_off;
+          pre_len = J.pre_len; total = J.pre_len + J.in_len;
+          out_cap = J.out_cap; opos = 0; low = 1; high = 0xFFFFFFFFu;
+          c = 0; cb = fetch(0); cbn = fetch(1);
+          st = 1;
+        }
+      }
+    }
+    const bool ready = st == 1 && sync->qfin >= c + CD;
+    if (!__any_sync(ZPQ_FULL, ready)) {
+      if (__all_sync(ZPQ_FULL, st == 3)) break;
+      __nanosleep(200);
+      continue;
+    }
+    if (LS.hold(st == 1, ready)) continue;
+    if (ready) {
+      __threadfence_block();
+      sync->cpos = c;
+      ++low;                         // encode(0, 0) in front of every byte, Encoder.cs:49
+      normalise();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int pf = pfring[(c * 8u + k) & (kDuoRing - 1)];
+        const uint32_t pr = (uint32_t)S.squash[pf + 2048] * 2 + 1;
+        const uint32_t mid = low + (uint32_t)(((uint64_t)(high - low) * pr) >> 16);
+        if ((cb >> (7 - k)) & 1) high = mid; else low = mid + 1;
+        normalise();
+      }
+      ++c; cb = cbn; cbn = fetch(c + 1);
+      if (c == total) {
+        high = low;                  // encode(1, 0), Encoder.cs:46
+        normalise();
+        uint32_t status = sync->lstatus;
+        if (opos > out_cap) status = BLK_OVERFLOW;
+        P.results[job].out_len = opos; P.results[job].status = status;
+        __threadfence_block();
+        sync->cdone = seq;
+        st = 0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Kernel body: warp 0 = arithmetic coder of every block of the CTA; warp 1+2p = lead role, warp 2+2p = coder
+// (prediction) role of block group p.
+template <class DM>
+__device__ __forceinline__ void encode_duo_body(const CodecParams& P, uint8_t* smem) {
+  Shared S;
+  stage_shared(P, smem, S);
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) duo_arith_body<DM>(P, smem, S);
+  else if ((warp - 1) & 1) duo_coder_body<DM>(P, smem, S, (warp - 1) >> 1);
+  else duo_lead_body<DM>(P, smem, S, (warp - 1) >> 1);
+}
+
+}  // namespace zpq

@@ -134,7 +134,7 @@ void build_tables(Tables& t) {
 }
 
 // ------------------------------------------------------------------------------------------
-void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl) {
+void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl, int duo_g) {
   memset(&pl, 0, sizeof(Plan) - sizeof(pl.hcomp));
   pl.n = h.n; pl.hh = h.hh; pl.hm = h.hm; pl.ph = h.ph; pl.pm = h.pm;
   if (h.hh > 28 || h.hm > 30 || h.ph > 28 || h.pm > 30)
@@ -146,19 +146,27 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   uint64_t arena = 0;
   auto take = [&](uint64_t bytes) { uint64_t o = arena; arena = align_up(arena + bytes, 256); return o; };
   int ninit = 0;
-  auto fill = [&](uint64_t dst, uint64_t bytes, uint8_t kind, uint32_t value, bool smem) {
+  // role: which warp of the two-role encoder owns (and initialises) the table -- 0 lead, 1 coder
+  auto fill = [&](uint64_t dst, uint64_t bytes, uint8_t kind, uint32_t value, bool smem, uint8_t role = 0) {
     InitOp& op = pl.init[ninit++];
-    op.dst = dst; op.bytes = align_up(bytes, 16); op.kind = kind; op.value = value; op.to_smem = smem; op.pad = 0;
+    op.dst = dst; op.bytes = align_up(bytes, 16); op.kind = kind; op.value = value; op.to_smem = smem; op.role = role; op.pad = 0;
   };
 
   // shared slice: p[n], state[n] (5 words each), then optionally H and the small cm tables
   uint32_t slice = 0;
   auto stake = [&](uint32_t bytes) { uint32_t o = slice; slice = (uint32_t)align_up(slice + bytes, 16); return o; };
   const int nn = std::max(h.n, 1);
-  pl.smem_p = stake(4u * nn);
-  pl.smem_st = stake(20u * nn);
-  pl.smem_rows = stake(1024);   // 32 lanes x 16-byte row cache, twice (the skewed encoder requests rows a nibble ahead)
-  pl.smem_chain = stake(256);
+  pl.duo_g = duo_g;
+  if (duo_g) {
+    pl.smem_sync = stake(32);
+    pl.smem_pfring = stake(128);
+    pl.smem_rows = stake(32u * duo_g);   // duo_g lanes x 16-byte row cache, twice
+  } else {
+    pl.smem_p = stake(4u * nn);
+    pl.smem_st = stake(20u * nn);
+    pl.smem_rows = stake(1024);   // 32 lanes x 16-byte row cache, twice (the skewed encoder requests rows a nibble ahead)
+    pl.smem_chain = stake(256);
+  }
   // Pipelined encoder: component i works delay[i] bits behind the leading bit, strictly later than
   // everything it reads; a MIX additionally stays kPipeMixAhead bits back so that its weight rows
   // can be requested before they are needed.  The coder follows component n-1 by one bit.
@@ -172,7 +180,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         case C_AVG: in(q[1]); in(q[2]); break;
         case C_MIX2: in(q[2]); in(q[3]); break;
         case C_ISSE: case C_SSE: in(q[2]); break;
-        case C_MIX: for (int j = 0; j < q[3]; ++j) in(q[2] + j); dl = std::max(dl, kPipeMixAhead); break;
+        case C_MIX: for (int j = 0; j < q[3]; ++j) in(q[2] + j); dl = std::max(dl, duo_g ? kDuoMixAhead : kPipeMixAhead); break;
         default: break;
       }
       delay[i] = (uint8_t)std::min(dl, 255);
@@ -183,7 +191,38 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
     while ((int)pl.ring_slots <= pl.coder_delay) pl.ring_slots *= 2;
     pl.ring_stride = (uint32_t)align_up(nn, 8);
     pl.pipe_ok = h.n >= 1 && h.n <= 32 && pl.coder_delay <= kMaxPipeDelay;
-    if (pl.pipe_ok) {
+    // two-role encoder: predictions of lead-role components (CONS/CM/ICM/MATCH) are read from the ring at any
+    // distance; a prediction made by the coder role is read from its lane's history of the last 8 bits
+    {
+      auto lead_type = [&](int t) { return t == C_CONS || t == C_CM || t == C_ICM || t == C_MATCH; };
+      std::vector<int> types(h.n);
+      const uint8_t* q2 = &h.wire[7];
+      for (int i = 0; i < h.n; ++i) { types[i] = q2[0]; q2 += comp_len(q2[0]); }
+      int hdepth = 1, ldepth = 1;
+      q2 = &h.wire[7];
+      for (int i = 0; i < h.n; ++i) {
+        auto dep = [&](int j, bool lane_owned) {
+          if (j >= i || lead_type(types[j])) return;
+          hdepth = std::max(hdepth, delay[i] - delay[j]);
+          if (lane_owned) ldepth = std::max(ldepth, delay[i] - delay[j]);
+        };
+        switch (q2[0]) {
+          case C_AVG: dep(q2[1], true); dep(q2[2], true); break;
+          case C_MIX2: dep(q2[2], true); dep(q2[3], true); break;
+          case C_ISSE: case C_SSE: dep(q2[2], true); break;
+          case C_MIX: for (int j = 0; j < q2[3]; ++j) dep(q2[2] + j, false); break;
+          default: break;
+        }
+        q2 += comp_len(q2[0]);
+      }
+      pl.duo_hdepth = hdepth; pl.duo_ldepth = ldepth;
+      pl.duo_ok = duo_g && pl.pipe_ok && h.n <= duo_g && hdepth <= 8;
+    }
+    if (duo_g) {
+      pl.ring_slots = 64; pl.ring_stride = (uint32_t)duo_g;
+      pl.smem_pring = stake(2u * 64 * duo_g);
+      pl.smem_hsnap = stake(4u * 8 * duo_g);
+    } else if (pl.pipe_ok) {
       pl.smem_pring = stake(2u * pl.ring_slots * pl.ring_stride);
       pl.smem_bhring = stake(pl.ring_slots * pl.ring_stride);
       pl.smem_hsnap = stake(4u * 8 * pl.ring_stride);
@@ -223,7 +262,10 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (bits > 26) throw Failure(ZPQ_E_CONFIG, "max size for ICM is 26");
         d.mask = (uint32_t)((64ull << bits) - 16);
         d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false);
-        if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 1, 0, true); }
+        if (duo_g) {   // the lead role owns ICM maps and addresses them with a 4-byte stride
+          if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 4, 0, true); }
+          else { d.tab2 = take(1024); fill(d.tab2, 1024, 4, 0, false); }
+        } else if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 1, 0, true); }
         else { d.tab2 = take(2048); fill(d.tab2, 2048, 1, 0, false); }
         break;
       case C_MATCH:
@@ -243,7 +285,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (cp[3] >= i) throw Failure(ZPQ_E_CONFIG, "MIX2 k >= i");
         if (cp[2] >= i) throw Failure(ZPQ_E_CONFIG, "MIX2 j >= i");
         d.mask = (1u << bits) - 1;
-        d.tab = take(2ull << bits); fill(d.tab, 2ull << bits, 0, 0x80008000u, false);
+        d.tab = take(2ull << bits); fill(d.tab, 2ull << bits, 0, 0x80008000u, false, 1);
         level = 1 + std::max(lvl(cp[2]), lvl(cp[3]));
         break;
       case C_MIX: {
@@ -253,7 +295,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         const int m = cp[3];
         d.mask = (1u << bits) - 1;
         d.coop = 1;
-        d.tab = take((4ull * m) << bits); fill(d.tab, (4ull * m) << bits, 0, (uint32_t)(65536 / m), false);
+        d.tab = take((4ull * m) << bits); fill(d.tab, (4ull * m) << bits, 0, (uint32_t)(65536 / m), false, 1);
         for (int j = 0; j < m; ++j) level = std::max(level, 1 + lvl(cp[2] + j));
         break;
       }
@@ -262,8 +304,8 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (cp[2] >= i) throw Failure(ZPQ_E_CONFIG, "ISSE j >= i");
         d.mask = (uint32_t)((64ull << bits) - 16);
         d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false);
-        if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 2, 0, true); }
-        else { d.tab2 = take(2048); fill(d.tab2, 2048, 2, 0, false); }
+        if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 2, 0, true, 1); }
+        else { d.tab2 = take(2048); fill(d.tab2, 2048, 2, 0, false, 1); }
         level = 1 + lvl(cp[2]);
         break;
       case C_SSE:
@@ -271,7 +313,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (cp[2] >= i) throw Failure(ZPQ_E_CONFIG, "SSE j >= i");
         if (cp[3] > cp[4] * 4) throw Failure(ZPQ_E_CONFIG, "SSE start > limit*4");
         d.mask = (uint32_t)((32ull << bits) - 1);
-        d.tab = take(128ull << bits); fill(d.tab, 128ull << bits, 3, cp[3], false);
+        d.tab = take(128ull << bits); fill(d.tab, 128ull << bits, 3, cp[3], false, 1);
         level = 1 + lvl(cp[2]);
         break;
       default: throw Failure(ZPQ_E_CONFIG, "unknown component type");

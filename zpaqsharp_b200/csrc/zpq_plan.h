@@ -41,9 +41,10 @@ struct InitOp {
   uint64_t dst;        // arena byte offset, or shared-slice offset when to_smem
   uint64_t bytes;      // multiple of 16
   uint32_t value;      // fill word (kind 0) / SSE start count (kind 3)
-  uint8_t kind;        // 0 = constant word, 1 = ICM cm template, 2 = ISSE cm template, 3 = SSE pattern
+  uint8_t kind;        // 0 = constant word, 1 = ICM cm template, 2 = ISSE cm template, 3 = SSE pattern, 4 = compact ICM cm (4-byte stride)
   uint8_t to_smem;
-  uint16_t pad;
+  uint8_t role;        // two-role encoder (zpq_duo.cuh): 0 = table of the lead role, 1 = table of the coder role
+  uint8_t pad;
 };
 
 // One step of the per-bit prediction schedule.
@@ -68,6 +69,7 @@ constexpr int kMaxMix = 16;
 constexpr int kMixRegs = 4;   // MIX components whose weights a specialised kernel keeps in registers
 constexpr int kMaxPipeDelay = 23;   // the pipelined encoder keeps the last 32 coded bits in one register
 constexpr int kPipeMixAhead = 2;    // MIX rows are loaded this many bits before they are used
+constexpr int kDuoMixAhead = 4;     // ... in the two-role encoder, whose ticks are shorter than an L2 round trip
 
 struct Plan {
   int32_t n;                    // components
@@ -93,6 +95,13 @@ struct Plan {
   uint32_t smem_pring;          // int16 stretched predictions
   uint32_t smem_bhring;         // uint8 bit histories of ICM/ISSE components
   uint32_t smem_hsnap;          // uint32 contexts H[i] of the last 8 bytes (ring of 8 x ring_stride)
+  // two-role encoder (zpq_duo.cuh): slice laid out for groups of duo_g lanes per block
+  int32_t duo_g;                // 0: standard slice layout; 8/16/32: lanes per block in each role warp
+  int32_t duo_ok;               // 1: the two-role encoder applies to this model with this slice layout
+  int32_t duo_hdepth;           // deepest look-back into a lane's own prediction history (<= 8)
+  int32_t duo_ldepth;           // deepest look-back of a lane-owned consumer (ISSE/AVG/MIX2/SSE)
+  uint32_t smem_sync;           // DuoSync words of the block
+  uint32_t smem_pfring;         // int16 [64]: final stretched prediction per bit, for the arithmetic coder warp
   MixDesc mix[kMaxMix];
   CompDesc comp[kMaxComp];
   uint8_t order[kMaxComp];      // components sorted by (level, coop)
@@ -161,6 +170,7 @@ struct CodecParams {
   uint32_t njobs;
   uint32_t resident;          // warps that take part
   uint32_t* queue;            // next block index (atomic)
+  uint32_t wb;                // two-role encoder: blocks per CTA
   SmemLayout sm;
 };
 
