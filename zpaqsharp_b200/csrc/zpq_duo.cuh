@@ -43,6 +43,20 @@ struct DuoSync {              // per block, in its shared slice
   volatile uint32_t cpos;     // byte the arithmetic coder is working on
 };
 
+// ZPQ_DUO_TIMING: each role warp of CTA 0 prints the cycles it spent inside its byte loop bodies and in total
+#ifdef ZPQ_DUO_TIMING
+#include <stdio.h>
+#define ZPQ_T_DECL long long zt_busy = 0, zt_iters = 0, zt_fast = 0; const long long zt_begin = clock64();
+#define ZPQ_T_IN const long long zt_in = clock64();
+#define ZPQ_T_OUT(isfast) { zt_busy += clock64() - zt_in; ++zt_iters; zt_fast += (isfast) ? 1 : 0; }
+#define ZPQ_T_REPORT(name) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) printf("%s warp %d: busy %lld cycles in %lld byte steps (%lld fast) = %.1f per step; total %lld\n", name, (int)(threadIdx.x >> 5), zt_busy, zt_iters, zt_fast, zt_iters ? (double)zt_busy / zt_iters : 0.0, clock64() - zt_begin);
+#else
+#define ZPQ_T_DECL
+#define ZPQ_T_IN
+#define ZPQ_T_OUT(isfast)
+#define ZPQ_T_REPORT(name)
+#endif
+
 constexpr uint32_t kDuoRing = 64;     // bits of lead-role output kept per block
 constexpr uint32_t kDuoRetire = 0xFFFFFFFFu;
 
@@ -281,6 +295,7 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
 
   constexpr uint32_t DB = ((uint32_t)DM::D + 7u) / 8u;   // bytes the coder role reads back behind its own byte
   Lockstep LS;
+  ZPQ_T_DECL
   for (;;) {
     // ---- job management (warp-convergent) ----
     if (C.st == 2 && C.sync->cdone == C.seq) C.st = 0;
@@ -332,6 +347,7 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
       continue;
     }
     if (LS.hold(C.st == 1, run)) continue;
+    ZPQ_T_IN
     if (run) {
       duo_lead_tick<DM, 0>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
       duo_lead_tick<DM, 1>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
@@ -344,12 +360,14 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
       ++C.s;
     }
     __syncwarp();
+    ZPQ_T_OUT(__all_sync(ZPQ_FULL, run || C.st == 3))
     __threadfence_block();
     if (run) {
       if (gl == 0) { if (C.status) C.sync->lstatus = C.status; C.sync->lpos = C.s; }
       if (C.s == C.total) C.st = 2;
     }
   }
+  ZPQ_T_REPORT("lead")
 }
 
 // ==========================================================================================
@@ -416,9 +434,19 @@ struct MixDuo {
     constexpr bool kDistinct = CMASK == 255u && MASK >= 255u;
     constexpr int kBit = (KT - DM_) & 7;
     int wcur = r.mq[K][0];
+    if (!(kDistinct && kBit >= A)) {
+      // A hit is rare (it needs equal context hashes in consecutive bytes), and testing for it under a warp-uniform
+      // branch keeps the weight independent of the previous ticks' training in the common case.
+      bool hit = false;
 #pragma unroll
-    for (int j = A - 1; j >= 0; --j)
-      if (!(kDistinct && j < kBit)) wcur = r.mto[K][j] == r.mqo[K][0] ? r.mt[K][j] : wcur;
+      for (int j = 0; j < A; ++j)
+        if (!(kDistinct && j < kBit)) hit = hit || r.mto[K][j] == r.mqo[K][0];
+      if (__any_sync(gmask, hit)) {
+#pragma unroll
+        for (int j = A - 1; j >= 0; --j)
+          if (!(kDistinct && j < kBit)) wcur = r.mto[K][j] == r.mqo[K][0] ? r.mt[K][j] : wcur;
+      }
+    }
     const int acc = grp_sum<G>(gmask, (wcur >> 8) * pin);
     const int pm = clamp2k(acc >> 8);
     const int y = (int)((C.bits >> DM_) & 1);
@@ -602,6 +630,7 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
   C.st = valid ? 0 : 3;
   Hist H; H.h0 = H.h1 = 0;
   Lockstep LS;
+  ZPQ_T_DECL
   __syncthreads();   // pairs with the lead role: sync words are initialised
 
   for (;;) {
@@ -658,6 +687,7 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
     if (run) { __threadfence_block(); if (gl == 0) C.sync->qpos = C.s; }
     __syncwarp();   // the lanes must be CONVERGED when they enter the fast path: its shuffles are whole-warp
     const bool fast = __all_sync(ZPQ_FULL, steady || !live);
+    ZPQ_T_IN
     if (fast) {
       duo_coder_tick<DM, 0, true>(S, C, r, L, H, gl, gmask, gbase, live);
       duo_coder_tick<DM, 1, true>(S, C, r, L, H, gl, gmask, gbase, live);
@@ -678,6 +708,7 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
       duo_coder_tick<DM, 7, false>(S, C, r, L, H, gl, gmask, gbase, true);
     }
     __syncwarp();
+    ZPQ_T_OUT(fast)
     __threadfence_block();
     if (run) {
       ++C.s;
@@ -685,6 +716,7 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
       if (C.T >= C.NB + D) C.st = 0;     // every prediction of the block is in the ring
     }
   }
+  ZPQ_T_REPORT("coder")
 }
 
 // ==========================================================================================
@@ -705,6 +737,7 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
   const int16_t* pfring = reinterpret_cast<const int16_t*>(slice + plan->smem_pfring);
   int st = valid ? 0 : 3;
   Lockstep LS;
+  ZPQ_T_DECL
   uint32_t seq = 0, job = 0, c = 0, total = 0, pre_len = 0, cb = 0, cbn = 0, low = 1, high = 0xFFFFFFFFu;
   const uint8_t* in = P.in; uint8_t* out = P.out;
   uint64_t out_cap = 0, opos = 0;
@@ -749,6 +782,7 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
       continue;
     }
     if (LS.hold(st == 1, ready)) continue;
+    ZPQ_T_IN
     if (ready) {
       __threadfence_block();
       sync->cpos = c;
@@ -775,7 +809,9 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
       }
     }
     __syncwarp();
+    ZPQ_T_OUT(__all_sync(ZPQ_FULL, ready || st != 1))
   }
+  ZPQ_T_REPORT("arith")
 }
 
 // Kernel body: warp 0 = arithmetic coder of every block of the CTA; warp 1+2p = lead role, warp 2+2p = coder

@@ -69,7 +69,7 @@ constexpr int kMaxMix = 16;
 constexpr int kMixRegs = 4;   // MIX components whose weights a specialised kernel keeps in registers
 constexpr int kMaxPipeDelay = 23;   // the pipelined encoder keeps the last 32 coded bits in one register
 constexpr int kPipeMixAhead = 2;    // MIX rows are loaded this many bits before they are used
-constexpr int kDuoMixAhead = 4;     // ... in the two-role encoder, whose ticks are shorter than an L2 round trip
+constexpr int kDuoMixAhead = 6;     // ... in the two-role encoder, whose ticks are shorter than an L2 round trip
 
 struct Plan {
   int32_t n;                    // components
