@@ -136,6 +136,9 @@ struct LeadCtx {
   uint32_t pre_len, total, s, seq, status;
   uint32_t cb0, cb1, cb2, hnext;
   int st;                    // 0 idle, 1 running, 2 all bytes done (waiting for the coder role), 3 retired
+#ifdef ZPQ_DUO_TIMING
+  long long zt_k0 = 0, zt_bit = 0, zt_b7 = 0, zt_adv = 0;
+#endif
   __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
     if (i < pre_len) return preamble[i];
     return i < total ? in[i - pre_len] : 0u;
@@ -180,6 +183,9 @@ __device__ __forceinline__ void duo_lead_tick(const Shared& S, LeadCtx<DM::G>& C
   const bool hashed = (r.type == C_ICM || r.type == C_ISSE);
   const uint32_t s = C.s;
   if (K == 0) {
+#ifdef ZPQ_DUO_TIMING
+    const long long zt0 = clock64();
+#endif
     // ---- byte s begins: contexts were written when byte s-1 began ----
     C.cb2 = C.fetch(s + 2);
     r.h = C.hsnap[(s & 7) * G + gl];
@@ -200,7 +206,13 @@ __device__ __forceinline__ void duo_lead_tick(const Shared& S, LeadCtx<DM::G>& C
     }
     if (r.type == C_MATCH) prefetch_l2(reinterpret_cast<const uint32_t*>(r.tab) + (hn & r.mask));
     DM::prefetch(r, hn, C.cb1, gl, gmask, gbase);
+#ifdef ZPQ_DUO_TIMING
+    C.zt_k0 += clock64() - zt0;
+#endif
   }
+#ifdef ZPQ_DUO_TIMING
+  const long long zt1 = clock64();
+#endif
   const int y = (int)((C.cb0 >> (7 - K)) & 1);
   int val = 0;
   if (DM::HAS_HASHED) {
@@ -236,6 +248,10 @@ __device__ __forceinline__ void duo_lead_tick(const Shared& S, LeadCtx<DM::G>& C
     if (r.type == C_CONS) val = ((int)r.a1 - 128) * 4;         // Predictor.cs:96-98
   }
   C.lring[((s * 8u + K) & (kDuoRing - 1)) * G + gl] = (int16_t)val;
+#ifdef ZPQ_DUO_TIMING
+  if (K == 7) C.zt_b7 += clock64() - zt1; else C.zt_bit += clock64() - zt1;
+  const long long zt2 = clock64();
+#endif
   // ---- shift the bit into c8 / hmap4 (Predictor.cs:463-474) ----
   const int c8 = C.w.c8 * 2 + y;
   if (K == 7) {
@@ -252,6 +268,9 @@ __device__ __forceinline__ void duo_lead_tick(const Shared& S, LeadCtx<DM::G>& C
   }
   if (K == 7 && hashed) find_resolve(F, row2);                 // requested at bit 3; swapped in when the next byte begins
   C.w.c8 = c8;
+#ifdef ZPQ_DUO_TIMING
+  C.zt_adv += clock64() - zt2;
+#endif
 }
 
 template <class DM>
@@ -368,6 +387,9 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
     }
   }
   ZPQ_T_REPORT("lead")
+#ifdef ZPQ_DUO_TIMING
+  if (blockIdx.x == 0 && lane == 0) printf("  lead split: byte-start %lld, bits0-6 %lld, bit7 %lld, advance/find %lld\n", C.zt_k0, C.zt_bit, C.zt_b7, C.zt_adv);
+#endif
 }
 
 // ==========================================================================================
