@@ -141,6 +141,7 @@ struct Launch {
   bool skewed = false;     // encode with the time-skewed kernel (zpq_pipe.cuh)
   bool duo = false;        // encode with the two-role kernel (zpq_duo.cuh)
   uint32_t wb = 0;         // ... blocks per CTA
+  uint32_t duo_roles = 3;  // ... role warps per block group (context, history, coder[, mixer])
   std::string kernel;      // what will run (for zpq_stats)
 };
 
@@ -188,7 +189,13 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
     // Two-role encoder (zpq_duo.cuh): 32/G blocks share a pair of warps, up to 7 pairs per SM plus one
     // arithmetic coder warp (lane = block, so at most 32 blocks); every ICM/ISSE map has to live in the block's shared slice.
     const uint32_t G = (uint32_t)spec.duo_g, B = 32 / G;
-    uint64_t res = std::min<uint64_t>({want, fit, (uint64_t)d.sms * std::min(7u * B, 32u)});
+    {
+      std::unique_ptr<Plan> probe(new Plan);
+      build_plan(hdr, false, 48 * 1024, *probe, (int)G);
+      L.duo_roles = probe->duo_split ? 4 : 3;
+    }
+    const uint32_t max_groups = 15u / L.duo_roles;     // 16 warps per CTA, one of them the arithmetic coder
+    uint64_t res = std::min<uint64_t>({want, fit, (uint64_t)d.sms * std::min(max_groups * B, 32u)});
     if (max_resident) res = std::min<uint64_t>(res, max_resident);
     if (res < 1) res = 1;
     uint32_t wb = (uint32_t)((res + d.sms - 1) / d.sms);
@@ -204,10 +211,10 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
       L.sm.slice_bytes = L.plan->smem_warp_bytes;
       L.sm.total = L.sm.slices + wb * L.sm.slice_bytes;
       L.wb = wb;
-      L.geom.warps_per_cta = 1 + 2 * ((wb + B - 1) / B);
+      L.geom.warps_per_cta = 1 + L.duo_roles * ((wb + B - 1) / B);
       L.geom.lanes = 1;
       L.has_spec = true; L.spec = spec;
-      L.kernel = std::string("duo/") + spec.origin + ", two-role x" + std::to_string(B) + " blocks per warp pair";
+      L.kernel = std::string("duo/") + spec.origin + ", " + std::to_string(L.duo_roles) + " roles + coder warp, x" + std::to_string(B) + " blocks per warp";
       L.geom.grid = (uint32_t)((res + wb - 1) / wb);
       L.resident = (uint32_t)res;
       return;

@@ -350,21 +350,21 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
       << "  static constexpr bool HAS_HASHED = " << ((tmask[C_ICM] | tmask[C_ISSE]) ? "true" : "false") << ", HAS_MATCH = " << (tmask[C_MATCH] ? "true" : "false")
       << ", HAS_CM = " << (tmask[C_CM] ? "true" : "false") << ", HAS_CONS = " << (tmask[C_CONS] ? "true" : "false")
       << ", HAS_ISSE = " << (tmask[C_ISSE] ? "true" : "false") << ", NEEDK = " << ((tmask[C_AVG] | tmask[C_MIX2]) ? "true" : "false")
-      << ", FINAL_MIX = " << (pl.comp[pl.n - 1].type == C_MIX ? "true" : "false") << ";\n";
+      << ", FINAL_MIX = " << (pl.comp[pl.n - 1].type == C_MIX ? "true" : "false") << ", SPLIT = " << (pd.duo_split ? "true" : "false") << ";\n";
     for (int k = 0; k < pl.nmix; ++k)
       if (mix_regs)
         o << "  typedef MixDuo<" << G << ", " << k << ", " << (int)pl.mix[k].lane << ", " << (int)pl.mix[k].j0 << ", " << (int)pl.mix[k].m << ", "
           << (int)pl.mix[k].rate << ", " << pl.mix[k].mask << "u, " << (int)pl.mix[k].cmask << "u, " << (int)pd.comp[pl.mix[k].lane].delay
-          << ", LMASK> QMix" << k << ";\n";
+          << ", LMASK, " << ((int)pl.mix[k].lane == pl.n - 1 ? "true" : "false") << "> QMix" << k << ";\n";
     o << "  static __device__ __forceinline__ void lanes(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, int pj, int pk, int y, bool act, uint32_t t, int& p, int lane) {\n";
     if (tmask[C_AVG]) o << "    if (" << lane_test(tmask[C_AVG]) << ") duo_avg<G>(r, pj, pk, act, p);\n";
     if (tmask[C_MIX2]) o << "    if (" << lane_test(tmask[C_MIX2]) << ") duo_mix2<G>(S, C, r, pj, pk, y, act, t, p, lane);\n";
     if (tmask[C_SSE]) o << "    if (" << lane_test(tmask[C_SSE]) << ") duo_sse<G>(S, C, r, pj, y, act, t, p, lane);\n";
     o << "  }\n";
-    o << "  template <bool FAST, int KT> static __device__ __forceinline__ void mixes(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, const Hist& H, int& p, int& pmv, int lane, uint32_t gmask, int gbase, bool live) {\n";
+    o << "  template <bool FAST, int KT, bool RING> static __device__ __forceinline__ void mixes(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, const Hist& H, int& p, int& pmv, int lane, uint32_t gmask, int gbase, bool live, int krt) {\n";
     for (int k = 0; k < pl.nmix; ++k) {
-      if (mix_regs) o << "    QMix" << k << "::template tick<FAST, KT>(S, C, r, H, p, pmv, lane, gmask, gbase, live);\n";
-      else o << "    duo_mix_rt<G, LMASK>(S, S.mix[" << k << "], " << (int)pd.comp[pl.mix[k].lane].delay << ", C, r, H, p, pmv, lane, gmask, gbase, live);\n";
+      if (mix_regs) o << "    QMix" << k << "::template tick<FAST, KT, RING>(S, C, r, H, p, pmv, lane, gmask, gbase, live, krt);\n";
+      else o << "    duo_mix_rt<G, LMASK, RING>(S, S.mix[" << k << "], " << (int)pd.comp[pl.mix[k].lane].delay << ", C, r, H, p, pmv, lane, gmask, gbase, live);\n";
     }
     o << "  }\n";
     o << "  static __device__ __forceinline__ void prefetch(const LaneRegs& r, uint32_t hnext, uint32_t cnext, int lane, uint32_t gmask, int gbase) {\n";

@@ -33,7 +33,7 @@
 namespace zpq {
 
 struct DuoSync {              // per block, in its shared slice
-  volatile uint32_t lpos;     // bytes of the current job the lead role has finished
+  volatile uint32_t lpos;     // bytes of the current job the history role (hash rows, bit histories) has finished
   volatile uint32_t qpos;     // byte the coder role is working on
   volatile uint32_t jobseq;   // bumped by the lead role when it publishes a job
   volatile uint32_t jobid;    // that job; 0xFFFFFFFF = the queue is empty, retire
@@ -41,6 +41,10 @@ struct DuoSync {              // per block, in its shared slice
   volatile uint32_t lstatus;  // BLK_* raised by the lead role (ZPAQL error)
   volatile uint32_t qfin;     // bytes (ticks / 8) of the current job the coder role has finished
   volatile uint32_t cpos;     // byte the arithmetic coder is working on
+  volatile uint32_t mfin;     // mixer role (when the model has one): bytes finished
+  volatile uint32_t mpos;     // ... byte it is working on
+  volatile uint32_t lafin;    // bytes of the current job the context role (HCOMP, MATCH) has finished
+  uint32_t pad;
 };
 
 // ZPQ_DUO_TIMING: each role warp of CTA 0 prints the cycles it spent inside its byte loop bodies and in total
@@ -49,7 +53,7 @@ struct DuoSync {              // per block, in its shared slice
 #define ZPQ_T_DECL long long zt_busy = 0, zt_iters = 0, zt_fast = 0; const long long zt_begin = clock64();
 #define ZPQ_T_IN const long long zt_in = clock64();
 #define ZPQ_T_OUT(isfast) { zt_busy += clock64() - zt_in; ++zt_iters; zt_fast += (isfast) ? 1 : 0; }
-#define ZPQ_T_REPORT(name) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) printf("%s warp %d: busy %lld cycles in %lld byte steps (%lld fast) = %.1f per step; total %lld\n", name, (int)(threadIdx.x >> 5), zt_busy, zt_iters, zt_fast, zt_iters ? (double)zt_busy / zt_iters : 0.0, clock64() - zt_begin);
+#define ZPQ_T_REPORT(name) if (blockIdx.x % 16 == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 6) printf("cta %d %s warp %d: busy %lld cycles in %lld byte steps (%lld fast) = %.1f per step; total %lld\n", (int)blockIdx.x, name, (int)(threadIdx.x >> 5), zt_busy, zt_iters, zt_fast, zt_iters ? (double)zt_busy / zt_iters : 0.0, clock64() - zt_begin);
 #else
 #define ZPQ_T_DECL
 #define ZPQ_T_IN
@@ -136,9 +140,6 @@ struct LeadCtx {
   uint32_t pre_len, total, s, seq, status;
   uint32_t cb0, cb1, cb2, hnext;
   int st;                    // 0 idle, 1 running, 2 all bytes done (waiting for the coder role), 3 retired
-#ifdef ZPQ_DUO_TIMING
-  long long zt_k0 = 0, zt_bit = 0, zt_b7 = 0, zt_adv = 0;
-#endif
   __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
     if (i < pre_len) return preamble[i];
     return i < total ? in[i - pre_len] : 0u;
@@ -175,105 +176,108 @@ __device__ __forceinline__ void duo_match_byte(const WarpCtx& W, LaneRegs& r, in
   if (r.ma) r.mbyte = buf[(r.mpos - r.mb) & r.mask2];
 }
 
-// One bit of the lead role for the lane's component.  K = bit of the byte (0 = most significant).
-template <class DM, int K>
+// One bit of a lead role for the lane's component.  K = bit of the byte (0 = most significant).
+// The data-only work is split over two role warps:
+//   LR == 0  context role: HCOMP (contexts of the next byte), the MATCH component, and every L2 prefetch the
+//            contexts allow (hash rows, MATCH index slot, MIX rows) -- it also owns the job queue;
+//   LR == 1  history role: hash-row look-ups and bit histories of ICM/ISSE, the ICM maps, CM and CONS.
+// KC >= 0: the bit index is a compile-time constant (8 specialised copies per byte); KC < 0: it is the run-time
+// argument `krt` and the byte loop stays rolled -- one copy of the code, which is what the instruction caches
+// want when several role warps with different code share an SM (see ZPQ_DUO_UNROLL).
+template <class DM, int KC, int LR>
 __device__ __forceinline__ void duo_lead_tick(const Shared& S, LeadCtx<DM::G>& C, LaneRegs& r, FindAhead& F, uint8_t*& row2,
-                                               VM& vm, VMEnv& env, int gl, uint32_t gmask, int gbase) {
+                                               VM& vm, VMEnv& env, int gl, uint32_t gmask, int gbase, int krt) {
   constexpr int G = DM::G;
-  const bool hashed = (r.type == C_ICM || r.type == C_ISSE);
+  const int K = KC >= 0 ? KC : krt;
+  const bool hashed = LR == 1 && (r.type == C_ICM || r.type == C_ISSE);
   const uint32_t s = C.s;
   if (K == 0) {
-#ifdef ZPQ_DUO_TIMING
-    const long long zt0 = clock64();
-#endif
-    // ---- byte s begins: contexts were written when byte s-1 began ----
+    // ---- byte s begins ----
     C.cb2 = C.fetch(s + 2);
     r.h = C.hsnap[(s & 7) * G + gl];
     C.w.c8 = 1; C.w.hmap4 = 1;
-    if (hashed) {
-      if (s == 0) lane_find(r, r.h + 16);
-      else find_swap(r, F, row2, r.h + 16);
-      find_issue(r, r.h + 16u * (16u + (C.cb0 >> 4)), F);      // second nibble of this byte
+    if (LR == 1) {
+      C.hnext = C.hsnap[((s + 1) & 7) * G + gl];               // written by the context role during its byte s
+      if (hashed) {
+        if (s == 0) lane_find(r, r.h + 16);
+        else find_swap(r, F, row2, r.h + 16);
+        find_issue(r, r.h + 16u * (16u + (C.cb0 >> 4)), F);    // second nibble of this byte
+      }
+    } else {
+      // contexts of byte s+1 (HCOMP sees byte s, ZPAQL.cs:1253-1265) and the lines that byte will touch
+      if (DM::hcomp(S, C.w, vm, env, C.cb0, gl, gmask)) C.status = BLK_ZPAQL;
+      const uint32_t hn = C.w.H[gl & C.w.hmask];
+      C.hsnap[((s + 1) & 7) * G + gl] = hn;
+      C.hnext = hn;
+      if (r.type == C_ICM || r.type == C_ISSE) {
+        prefetch_l2(r.tab + (((hn + 16u) * 16u) & r.mask));
+        prefetch_l2(r.tab + (((hn + 16u * (16u + (C.cb1 >> 4))) * 16u) & r.mask));
+      }
+      if (r.type == C_MATCH) prefetch_l2(reinterpret_cast<const uint32_t*>(r.tab) + (hn & r.mask));
+      DM::prefetch(r, hn, C.cb1, gl, gmask, gbase);
     }
-    // contexts of byte s+1 (HCOMP sees byte s, ZPAQL.cs:1253-1265) and the lines that byte will touch
-    if (DM::hcomp(S, C.w, vm, env, C.cb0, gl, gmask)) C.status = BLK_ZPAQL;
-    const uint32_t hn = C.w.H[gl & C.w.hmask];
-    C.hsnap[((s + 1) & 7) * G + gl] = hn;
-    C.hnext = hn;
-    if (hashed) {
-      prefetch_l2(r.tab + (((hn + 16u) * 16u) & r.mask));
-      prefetch_l2(r.tab + (((hn + 16u * (16u + (C.cb1 >> 4))) * 16u) & r.mask));
-    }
-    if (r.type == C_MATCH) prefetch_l2(reinterpret_cast<const uint32_t*>(r.tab) + (hn & r.mask));
-    DM::prefetch(r, hn, C.cb1, gl, gmask, gbase);
-#ifdef ZPQ_DUO_TIMING
-    C.zt_k0 += clock64() - zt0;
-#endif
   }
-#ifdef ZPQ_DUO_TIMING
-  const long long zt1 = clock64();
-#endif
   const int y = (int)((C.cb0 >> (7 - K)) & 1);
   int val = 0;
-  if (DM::HAS_HASHED) {
-    // bit history of the slot this bit selects; ICM also predicts and learns here (Predictor.cs:267-272, 375-381).
-    // Straight-line on all lanes: lanes of other types read harmless dummies and store nothing.
-    const bool icm = r.type == C_ICM;
-    const uint32_t si = (uint32_t)C.w.hmap4 & 15u;
-    const uint32_t bh = r.row[si];
-    const uint32_t pn = r.cm[icm ? bh : 0u];
-    const uint32_t nx = S.ns[bh * 4 + y];
-    const int sp = S.stretch[(pn >> 8) & 32767u];
-    if (hashed) r.row[si] = (uint8_t)nx;
-    if (icm) r.cm[bh] = pn + (uint32_t)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
-    val = icm ? sp : (int)bh;
-  }
-  if (DM::HAS_MATCH) {                                          // Predictor.cs:273-287, 382-411
+  bool mine = false;
+  if (LR == 1) {
+    if (DM::HAS_HASHED) {
+      // bit history of the slot this bit selects; ICM also predicts and learns here (Predictor.cs:267-272, 375-381).
+      // Straight-line on all lanes: lanes of other types read harmless dummies and store nothing.
+      const bool icm = r.type == C_ICM;
+      const uint32_t si = (uint32_t)C.w.hmap4 & 15u;
+      const uint32_t bh = r.row[si];
+      const uint32_t pn = r.cm[icm ? bh : 0u];
+      const uint32_t nx = S.ns[bh * 4 + y];
+      const int sp = S.stretch[(pn >> 8) & 32767u];
+      if (hashed) r.row[si] = (uint8_t)nx;
+      if (icm) r.cm[bh] = pn + (uint32_t)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
+      val = icm ? sp : (int)bh;
+      mine = hashed;
+    }
+    if (DM::HAS_CM) {
+      if (r.type == C_CM) {                                    // Predictor.cs:263-266, 365-373
+        pa_cm(S, C.w, r);
+        val = r.p;
+        up_cm(S, r, y);
+        mine = true;
+      }
+    }
+    if (DM::HAS_CONS) {
+      if (r.type == C_CONS) { val = ((int)r.a1 - 128) * 4; mine = true; }   // Predictor.cs:96-98
+    }
+  } else if (DM::HAS_MATCH) {                                  // Predictor.cs:273-287, 382-411
     const bool mat = r.type == C_MATCH;
     if (K == 0 && mat) r.t0 = (int)reinterpret_cast<const uint32_t*>(r.tab)[r.h & r.mask];   // index slot of this byte's context, used at K == 7
     const uint32_t bit = (r.mbyte >> (7 - K)) & 1;
     const int pm = S.stretch[(S.dt2k[r.ma & 255u] * (1 - 2 * (int)bit)) & 32767];
-    val = mat ? (r.ma ? pm : 0) : val;
+    val = r.ma ? pm : 0;
     if (mat && (int)bit != y) r.ma = 0;
     if (K == 7 && mat) duo_match_byte(C.w, r, y);
+    mine = mat;
   }
-  if (DM::HAS_CM) {
-    if (r.type == C_CM) {                                      // Predictor.cs:263-266, 365-373
-      pa_cm(S, C.w, r);
-      val = r.p;
-      up_cm(S, r, y);
-    }
-  }
-  if (DM::HAS_CONS) {
-    if (r.type == C_CONS) val = ((int)r.a1 - 128) * 4;         // Predictor.cs:96-98
-  }
-  C.lring[((s * 8u + K) & (kDuoRing - 1)) * G + gl] = (int16_t)val;
-#ifdef ZPQ_DUO_TIMING
-  if (K == 7) C.zt_b7 += clock64() - zt1; else C.zt_bit += clock64() - zt1;
-  const long long zt2 = clock64();
-#endif
+  if (mine) C.lring[((s * 8u + K) & (kDuoRing - 1)) * G + gl] = (int16_t)val;
   // ---- shift the bit into c8 / hmap4 (Predictor.cs:463-474) ----
   const int c8 = C.w.c8 * 2 + y;
   if (K == 7) {
     C.cb0 = C.cb1; C.cb1 = C.cb2;
-  } else if (K == 3) {
-    C.w.hmap4 = (C.w.hmap4 & 0xf) << 5 | y << 4 | 1;
-    if (hashed) {
-      find_resolve(F, row2);                                   // requested when the byte began
-      find_swap(r, F, row2, r.h + 16u * (uint32_t)c8);
-      find_issue(r, C.hnext + 16u, F);                         // first nibble of the next byte
+  } else if (LR == 1) {
+    if (K == 3) {
+      C.w.hmap4 = (C.w.hmap4 & 0xf) << 5 | y << 4 | 1;
+      if (hashed) {
+        find_resolve(F, row2);                                 // requested when the byte began
+        find_swap(r, F, row2, r.h + 16u * (uint32_t)c8);
+        find_issue(r, C.hnext + 16u, F);                       // first nibble of the next byte
+      }
+    } else {
+      C.w.hmap4 = (C.w.hmap4 & 0x1f0) | (((C.w.hmap4 & 0xf) * 2 + y) & 0xf);
     }
-  } else {
-    C.w.hmap4 = (C.w.hmap4 & 0x1f0) | (((C.w.hmap4 & 0xf) * 2 + y) & 0xf);
   }
-  if (K == 7 && hashed) find_resolve(F, row2);                 // requested at bit 3; swapped in when the next byte begins
+  if (LR == 1 && K == 7 && hashed) find_resolve(F, row2);      // requested at bit 3; swapped in when the next byte begins
   C.w.c8 = c8;
-#ifdef ZPQ_DUO_TIMING
-  C.zt_adv += clock64() - zt2;
-#endif
 }
 
-template <class DM>
+template <class DM, int LR>
 __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* smem, const Shared& S, int pair) {
   constexpr int G = DM::G, B = 32 / G;
   const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G, gbase = lane & ~(G - 1);
@@ -309,87 +313,134 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
   env.out = nullptr; env.out_pos = 0; env.out_cap = 0;
   FindAhead F;
   F.r0 = F.r1 = F.r2 = make_uint4(0, 0, 0, 0); F.h0 = F.chk = F.at = 0; F.hz = true;
-  if (valid && gl == 0) { C.sync->lpos = 0; C.sync->qpos = 0; C.sync->jobid = 0; C.sync->cdone = 0; C.sync->lstatus = 0; C.sync->jobseq = 0; C.sync->qfin = 0; C.sync->cpos = 0; }
-  __syncthreads();   // the coder role reads the sync words from here on
+  if (LR == 0 && valid && gl == 0) {
+    C.sync->lpos = 0; C.sync->qpos = 0; C.sync->jobid = 0; C.sync->cdone = 0; C.sync->lstatus = 0; C.sync->jobseq = 0;
+    C.sync->qfin = 0; C.sync->cpos = 0; C.sync->mfin = 0; C.sync->mpos = 0; C.sync->lafin = 0;
+  }
+  __syncthreads();   // the other roles read the sync words from here on
 
-  constexpr uint32_t DB = ((uint32_t)DM::D + 7u) / 8u;   // bytes the coder role reads back behind its own byte
+  constexpr uint32_t DB = ((uint32_t)DM::D + 7u) / 8u;   // bytes the coder / mixer role reads back behind its own byte
   Lockstep LS;
   ZPQ_T_DECL
   for (;;) {
     // ---- job management (warp-convergent) ----
-    if (C.st == 2 && C.sync->cdone == C.seq) C.st = 0;
-    uint32_t want = __ballot_sync(ZPQ_FULL, C.st == 0 && gl == 0);
-    while (want) {
-      const int src = __ffs(want) - 1;
-      want &= want - 1;
-      uint32_t job = 0;
-      if (lane == src) job = atomicAdd(P.queue, 1u);
-      job = __shfl_sync(ZPQ_FULL, job, src);
-      const bool mine = gbase == src;
-      if (job >= P.njobs) {
-        if (mine) {
-          C.st = 3;
-          if (gl == 0) { C.sync->jobid = kDuoRetire; __threadfence_block(); C.sync->jobseq = C.seq + 1; }
+    if (LR == 0) {
+      // the context role owns the queue: a block is handed out when the arithmetic coder has finished the last one
+      if (C.st == 2 && C.sync->cdone == C.seq) C.st = 0;
+      uint32_t want = __ballot_sync(ZPQ_FULL, C.st == 0 && gl == 0);
+      while (want) {
+        const int src = __ffs(want) - 1;
+        want &= want - 1;
+        uint32_t job = 0;
+        if (lane == src) job = atomicAdd(P.queue, 1u);
+        job = __shfl_sync(ZPQ_FULL, job, src);
+        const bool mine = gbase == src;
+        if (job >= P.njobs) {
+          if (mine) {
+            C.st = 3;
+            if (gl == 0) { C.sync->jobid = kDuoRetire; __threadfence_block(); C.sync->jobseq = C.seq + 1; }
+          }
+          continue;
         }
-        continue;
+        const EncJob J = P.ejobs[job];
+        uint8_t* arena_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.arena, src));
+        uint8_t* slice_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.slice, src));
+        if (J.in_len != 0xFFFFFFFFu) init_block_state_role(plan, P.tab, arena_g, slice_g, lane, 0);   // ZPAQL.inith, MATCH tables
+        __syncwarp();
+        if (mine) {
+          C.in = P.in + J.in_off; C.pre_len = J.pre_len;
+          C.total = J.in_len == 0xFFFFFFFFu ? 0u : J.pre_len + J.in_len;
+          C.s = 0; C.status = BLK_OK; C.seq += 1;
+          r.cxt = r.c = r.ma = r.mb = r.mpos = r.h = 0; r.t0 = r.t1 = 0; r.p = 0; r.mbyte = 0; r.mbit = 0;
+          if (r.type == C_MATCH) r.tab2[0] = 1;                  // Predictor.cs:118
+          C.w.c8 = 1; C.w.hmap4 = 1;
+          vm.b = vm.c = vm.d = vm.f = 0;
+          if (gl < G) C.hsnap[gl] = 0;                           // contexts of byte 0 are H == 0
+          C.cb0 = C.fetch(0); C.cb1 = C.fetch(1); C.cb2 = 0;
+          C.st = C.total ? 1 : 2;
+        }
+        __syncwarp();
+        if (mine && gl == 0) {
+          C.sync->lpos = 0; C.sync->qpos = 0; C.sync->qfin = 0; C.sync->cpos = 0; C.sync->mfin = 0; C.sync->mpos = 0;
+          C.sync->lafin = 0; C.sync->lstatus = 0; C.sync->jobid = job;
+          __threadfence_block();
+          C.sync->jobseq = C.seq;
+        }
       }
-      const EncJob J = P.ejobs[job];
-      uint8_t* arena_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.arena, src));
-      uint8_t* slice_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.slice, src));
-      if (J.in_len != 0xFFFFFFFFu) init_block_state_role(plan, P.tab, arena_g, slice_g, lane, 0);   // Predictor.init + ZPAQL.inith
-      __syncwarp();
-      if (mine) {
-        C.in = P.in + J.in_off; C.pre_len = J.pre_len;
-        C.total = J.in_len == 0xFFFFFFFFu ? 0u : J.pre_len + J.in_len;
-        C.s = 0; C.status = BLK_OK; C.seq += 1;
-        r.cxt = r.c = r.ma = r.mb = r.mpos = r.h = 0; r.t0 = r.t1 = 0; r.p = 0; r.mbyte = 0; r.mbit = 0;
-        if (r.type == C_MATCH) r.tab2[0] = 1;                  // Predictor.cs:118
-        C.w.c8 = 1; C.w.hmap4 = 1;
-        vm.b = vm.c = vm.d = vm.f = 0;
-        F.hz = true;
-        if (gl < G) C.hsnap[gl] = 0;                           // contexts of byte 0 are H == 0
-        C.cb0 = C.fetch(0); C.cb1 = C.fetch(1); C.cb2 = 0;
-        C.st = C.total ? 1 : 2;
-      }
-      __syncwarp();
-      if (mine && gl == 0) {
-        C.sync->lpos = 0; C.sync->qpos = 0; C.sync->qfin = 0; C.sync->cpos = 0; C.sync->lstatus = 0; C.sync->jobid = job;
+    } else {
+      bool fresh = false;
+      if (C.st == 0 && C.sync->jobseq != C.seq) {
         __threadfence_block();
-        C.sync->jobseq = C.seq;
+        C.seq += 1;
+        const uint32_t job = C.sync->jobid;
+        C.status = job;            // (the job index, until the group has been set up)
+        if (job == kDuoRetire) C.st = 3; else fresh = true;
+      }
+      uint32_t want = __ballot_sync(ZPQ_FULL, fresh && gl == 0);
+      while (want) {
+        const int src = __ffs(want) - 1;
+        want &= want - 1;
+        const uint32_t job = __shfl_sync(ZPQ_FULL, C.status, src);
+        const EncJob J = P.ejobs[job];
+        const bool mine = gbase == src;
+        if (J.in_len == 0xFFFFFFFFu) continue;     // the pre-processing stage overflowed its slot: nothing to do
+        uint8_t* arena_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.arena, src));
+        uint8_t* slice_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.slice, src));
+        init_block_state_role(plan, P.tab, arena_g, slice_g, lane, 3);   // hash tables, ICM maps, CM (Predictor.cs:99-113, 146-149)
+        __syncwarp();
+        if (mine) {
+          C.in = P.in + J.in_off; C.pre_len = J.pre_len; C.total = J.pre_len + J.in_len;
+          C.s = 0; C.status = BLK_OK;
+          r.cxt = r.c = r.h = 0; r.t0 = r.t1 = 0; r.p = 0;
+          C.w.c8 = 1; C.w.hmap4 = 1;
+          F.hz = true;
+          C.cb0 = C.fetch(0); C.cb1 = C.fetch(1); C.cb2 = 0;
+          C.st = 1;
+        }
       }
     }
-    // ---- flow control: stay at most 6 - DB bytes ahead of the coder role ----
-    const bool run = C.st == 1 && C.s + DB <= C.sync->qpos + 6u;
+    // ---- flow control: stay at most 6 - DB bytes ahead of the last role that reads the rings; the history
+    //      role also needs the contexts of bytes s and s+1, i.e. the context role's byte s ----
+    bool run = C.st == 1 && C.s + DB <= (DM::SPLIT ? C.sync->mpos : C.sync->qpos) + 6u;
+    if (LR == 1) run = run && C.sync->lafin >= C.s + 1;
     if (!__any_sync(ZPQ_FULL, run)) {
       if (__all_sync(ZPQ_FULL, C.st == 3)) break;
-      __nanosleep(200);
+      __nanosleep(LR == 0 ? 200 : 100);
       continue;
     }
     if (LS.hold(C.st == 1, run)) continue;
     ZPQ_T_IN
     if (run) {
-      duo_lead_tick<DM, 0>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
-      duo_lead_tick<DM, 1>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
-      duo_lead_tick<DM, 2>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
-      duo_lead_tick<DM, 3>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
-      duo_lead_tick<DM, 4>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
-      duo_lead_tick<DM, 5>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
-      duo_lead_tick<DM, 6>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
-      duo_lead_tick<DM, 7>(S, C, r, F, row2, vm, env, gl, gmask, gbase);
+      if (LR == 1) __threadfence_block();
+#ifdef ZPQ_DUO_UNROLL
+      duo_lead_tick<DM, 0, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 0);
+      duo_lead_tick<DM, 1, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 1);
+      duo_lead_tick<DM, 2, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 2);
+      duo_lead_tick<DM, 3, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 3);
+      duo_lead_tick<DM, 4, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 4);
+      duo_lead_tick<DM, 5, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 5);
+      duo_lead_tick<DM, 6, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 6);
+      duo_lead_tick<DM, 7, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 7);
+#else
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) duo_lead_tick<DM, -1, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, k);
+#endif
       ++C.s;
     }
     __syncwarp();
     ZPQ_T_OUT(__all_sync(ZPQ_FULL, run || C.st == 3))
     __threadfence_block();
     if (run) {
-      if (gl == 0) { if (C.status) C.sync->lstatus = C.status; C.sync->lpos = C.s; }
-      if (C.s == C.total) C.st = 2;
+      if (LR == 0) {
+        if (gl == 0) { if (C.status) C.sync->lstatus = C.status; C.sync->lafin = C.s; }
+        if (C.s == C.total) C.st = 2;       // wait for the arithmetic coder to finish the block
+      } else {
+        if (gl == 0) C.sync->lpos = C.s;
+        if (C.s == C.total) C.st = 0;
+      }
     }
   }
-  ZPQ_T_REPORT("lead")
-#ifdef ZPQ_DUO_TIMING
-  if (blockIdx.x == 0 && lane == 0) printf("  lead split: byte-start %lld, bits0-6 %lld, bit7 %lld, advance/find %lld\n", C.zt_k0, C.zt_bit, C.zt_b7, C.zt_adv);
-#endif
+  ZPQ_T_REPORT(LR == 0 ? "context" : "history")
 }
 
 // ==========================================================================================
@@ -398,7 +449,7 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
 template <int G>
 struct CoderCtx {
   DuoSync* sync;
-  const int16_t* lring;
+  int16_t* lring;            // [bit & 63][G]: lead-role output; the coder role overwrites an entry with its own prediction once it has used it
   const uint32_t* hsnap;
   int16_t* pfring;           // [bit & 63] stretched prediction of the last component, for the arithmetic coder warp
   uint8_t* arena;
@@ -426,7 +477,8 @@ struct CoderLane {
 
 // MIX K evaluated by the group DM_ bits behind the lead (Predictor.cs:302-316, 427-439); see MixPipe.
 // LMASK: bit i set = component i is a lead-role component.
-template <int G, int K, int MIXLANE, int J0, int M, int RATE, unsigned MASK, unsigned CMASK, int DM_, unsigned LMASK>
+// FINAL: this MIX is the model's last component (its prediction goes to the arithmetic coder).
+template <int G, int K, int MIXLANE, int J0, int M, int RATE, unsigned MASK, unsigned CMASK, int DM_, unsigned LMASK, bool FINAL>
 struct MixDuo {
   static __device__ __forceinline__ uint32_t rowoff(const CoderCtx<G>& C, uint32_t t, uint32_t d, int gl) {
     const uint32_t h = C.hsnap[((t >> 3) & 7) * G + MIXLANE];
@@ -435,9 +487,12 @@ struct MixDuo {
   // FAST: every group of the warp is inside its block with all stages (no range tests, whole-warp collectives);
   // `live` = this group really owns a running block (false: it rides along and must not store).
   // KT = bit of the byte the LEAD stage is at (the tick index inside the byte).
-  template <bool FAST, int KT>
+  // RING: mixer role -- every input is read from the ring (the coder role has replaced its entries by its
+  // predictions), the output goes back into the ring (for a later MIX) and to the arithmetic coder's ring.
+  template <bool FAST, int KC, bool RING>
   static __device__ __forceinline__ void tick(const Shared& S, const CoderCtx<G>& C, LaneRegs& r, const Hist& H, int& p, int& pmv, int gl,
-                                               uint32_t gmask, int gbase, bool live) {
+                                               uint32_t gmask, int gbase, bool live, int krt) {
+    const int KT = KC >= 0 ? KC : krt;
     constexpr int A = kDuoMixAhead;
     const uint32_t tm = C.T - (uint32_t)DM_, t2 = tm + A;
     const bool on2 = FAST || t2 < C.NB, onm = FAST || tm < C.NB;
@@ -445,16 +500,19 @@ struct MixDuo {
     int n2 = 0;
     if (on2 && gl < M) n2 = *reinterpret_cast<const int*>(r.mixtab[K] + o2);
     // input j0+gl of bit tm: from the ring (lead-role component) or from its lane's history
-    int hv = H.at((DM_ - r.d - 1) & 7);
-    if (J0) hv = __shfl_sync(gmask, hv, gbase + ((J0 + gl) & (G - 1)));
+    int hv = 0;
+    if (!RING) {
+      hv = H.at((DM_ - r.d - 1) & 7);
+      if (J0) hv = __shfl_sync(gmask, hv, gbase + ((J0 + gl) & (G - 1)));
+    }
     const int lv = C.lring[(tm & (kDuoRing - 1)) * G + ((J0 + gl) & (G - 1))];
-    const int pin = gl < M ? (((LMASK >> ((J0 + gl) & 31)) & 1u) ? lv : hv) : 0;
+    const int pin = gl < M ? ((RING || ((LMASK >> ((J0 + gl) & 31)) & 1u)) ? lv : hv) : 0;
     // The row of bit tm was requested A ticks ago; a training of the last A bits that hit the same row has to be
     // forwarded (mt[j] = weight trained at bit tm-1-j).  With the whole partial byte in the row index
     // (CMASK == 255, >= 256 rows) rows of one byte are pairwise distinct, so only trainings of the PREVIOUS
     // byte can match: bit kBit of a byte checks j >= kBit only, and bits >= A of a byte check nothing.
     constexpr bool kDistinct = CMASK == 255u && MASK >= 255u;
-    constexpr int kBit = (KT - DM_) & 7;
+    const int kBit = (KT - DM_) & 7;
     int wcur = r.mq[K][0];
     if (!(kDistinct && kBit >= A)) {
       // A hit is rare (it needs equal context hashes in consecutive bytes), and testing for it under a warp-uniform
@@ -485,6 +543,10 @@ struct MixDuo {
     r.mq[K][A - 1] = n2; r.mqo[K][A - 1] = o2;
     if (gl == MIXLANE) p = pm;
     pmv = pm;
+    if (RING && gl == MIXLANE && onm && live) {
+      C.lring[(tm & (kDuoRing - 1)) * G + MIXLANE] = (int16_t)pm;
+      if (FINAL) C.pfring[tm & (kDuoRing - 1)] = (int16_t)pm;
+    }
   }
   // lead role, start of byte s: pull the 8 rows byte s+1 will use into L2 (lane k: row of bit k)
   static __device__ __forceinline__ void prefetch(const LaneRegs& r, uint32_t hnext, uint32_t cnext, int gl, uint32_t gmask, int gbase) {
@@ -499,18 +561,21 @@ struct MixDuo {
 };
 
 // MIX described at run time (more than kMixRegs mixers): weights read and written in place.
-template <int G, unsigned LMASK>
+template <int G, unsigned LMASK, bool RING>
 __device__ __forceinline__ void duo_mix_rt(const Shared& S, const MixDesc& md, int dm, const CoderCtx<G>& C, LaneRegs& r, const Hist& H,
                                             int& p, int& pmv, int gl, uint32_t gmask, int gbase, bool live) {
   const uint32_t tm = C.T - (uint32_t)dm;
   const uint32_t h = C.hsnap[((tm >> 3) & 7) * G + md.lane];
   const uint32_t rowi = ((h + (C.c8(tm, (uint32_t)dm) & md.cmask)) & md.mask) * md.m;
   int* wp = reinterpret_cast<int*>(C.arena + md.tab) + rowi + gl;
-  int hv = H.at((dm - r.d - 1) & 7);
-  hv = __shfl_sync(gmask, hv, gbase + ((md.j0 + gl) & (G - 1)));
+  int hv = 0;
+  if (!RING) {
+    hv = H.at((dm - r.d - 1) & 7);
+    hv = __shfl_sync(gmask, hv, gbase + ((md.j0 + gl) & (G - 1)));
+  }
   const int lv = C.lring[(tm & (kDuoRing - 1)) * G + ((md.j0 + gl) & (G - 1))];
   const bool on = live && tm < C.NB && gl < md.m;
-  const int pin = gl < md.m ? (((LMASK >> ((md.j0 + gl) & 31)) & 1u) ? lv : hv) : 0;
+  const int pin = gl < md.m ? ((RING || ((LMASK >> ((md.j0 + gl) & 31)) & 1u)) ? lv : hv) : 0;
   const int wv = on ? *wp : 0;
   const int pm = clamp2k(grp_sum<G>(gmask, (wv >> 8) * pin) >> 8);
   const int y = (int)((C.bits >> dm) & 1);
@@ -518,6 +583,10 @@ __device__ __forceinline__ void duo_mix_rt(const Shared& S, const MixDesc& md, i
   if (on) *wp = clamp512k(wv + ((err * pin + (1 << 12)) >> 13));
   if (gl == md.lane) p = pm;
   pmv = pm;
+  if (RING && gl == md.lane && live && tm < C.NB) {
+    C.lring[(tm & (kDuoRing - 1)) * G + md.lane] = (int16_t)pm;
+    if ((int)md.lane == (int)S.n - 1) C.pfring[tm & (kDuoRing - 1)] = (int16_t)pm;
+  }
 }
 
 // One bit of the coder role.  DM (generated by zpq_codegen.cpp) supplies the constants
@@ -526,10 +595,11 @@ __device__ __forceinline__ void duo_mix_rt(const Shared& S, const MixDesc& md, i
 //   DM::mixes<FAST, K>(S, C, r, H, p, pmv, gl, gmask, gbase, live)      every MIX
 // FAST: steady state of every group of the warp -- no range tests, whole-warp collectives, and the tick is one
 // basic block, so consecutive ISSE chain links and the MIX overlap.
-template <class DM, int K, bool FAST>
+template <class DM, int KC, bool FAST>
 __device__ __forceinline__ void duo_coder_tick(const Shared& S, CoderCtx<DM::G>& C, LaneRegs& r, const CoderLane& L, Hist& H, int gl,
-                                                uint32_t gmask_rt, int gbase, bool live) {
+                                                uint32_t gmask_rt, int gbase, bool live, int krt) {
   constexpr int G = DM::G;
+  const int K = KC >= 0 ? KC : krt;
   constexpr uint32_t D = (uint32_t)DM::D;
   const uint32_t gmask = FAST ? ZPQ_FULL : gmask_rt;
   if (K == 0) C.cb2 = C.fetch(C.s + 2);
@@ -579,10 +649,12 @@ __device__ __forceinline__ void duo_coder_tick(const Shared& S, CoderCtx<DM::G>&
   }
   DM::lanes(S, C, r, pj, pk, y, act, t, p, gl);
   int pmv = 0;
-  DM::template mixes<FAST, K>(S, C, r, H, p, pmv, gl, gmask, gbase, live);
+  if (!DM::SPLIT) DM::template mixes<FAST, KC, false>(S, C, r, H, p, pmv, gl, gmask, gbase, live, krt);
   H.push(p);
+  // mixer role present: it reads this lane's prediction of bit t from the ring entry the lead role used for it
+  if (DM::SPLIT && act && !((DM::LMASK >> gl) & 1u) && r.type != C_MIX) C.lring[slot + gl] = (int16_t)p;
   // the last component's prediction of bit t goes to the arithmetic coder warp
-  if (gl == DM::N - 1 && act) C.pfring[t & (kDuoRing - 1)] = (int16_t)p;
+  if (!(DM::SPLIT && DM::FINAL_MIX) && gl == DM::N - 1 && act) C.pfring[t & (kDuoRing - 1)] = (int16_t)p;
   if (K == 7) { C.cb0 = C.cb1; C.cb1 = C.cb2; }
   ++C.T;
 }
@@ -614,7 +686,23 @@ __device__ __forceinline__ void duo_sse(const Shared& S, const CoderCtx<G>& C, L
   up_sse(S, r, y);
 }
 
-template <class DM>
+// One bit of the mixer role (models whose MIX components nothing lane-owned reads, DM::SPLIT): every MIX of the
+// model, inputs from the ring, weights requested kDuoMixAhead bits ahead, output to the arithmetic coder's ring.
+template <class DM, int KC, bool FAST>
+__device__ __forceinline__ void duo_mix_tick(const Shared& S, CoderCtx<DM::G>& C, LaneRegs& r, int gl, uint32_t gmask_rt, int gbase, bool live, int krt) {
+  const uint32_t gmask = FAST ? ZPQ_FULL : gmask_rt;
+  const int K = KC >= 0 ? KC : krt;
+  if (K == 0) C.cb2 = C.fetch(C.s + 2);
+  C.bits = C.bits << 1 | ((C.cb0 >> (7 - K)) & 1u);
+  Hist H; H.h0 = H.h1 = 0;
+  int p = 0, pmv = 0;
+  DM::template mixes<FAST, KC, true>(S, C, r, H, p, pmv, gl, gmask, gbase, live, krt);
+  if (K == 7) { C.cb0 = C.cb1; C.cb1 = C.cb2; }
+  ++C.T;
+}
+
+// ROLE 1: coder (prediction) role; ROLE 2: mixer role (only launched when DM::SPLIT).
+template <class DM, int ROLE>
 __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* smem, const Shared& S, int pair) {
   constexpr int G = DM::G, B = 32 / G;
   constexpr uint32_t D = (uint32_t)DM::D;
@@ -642,7 +730,7 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
   }
   CoderCtx<G> C;
   C.sync = reinterpret_cast<DuoSync*>(w.slice + plan->smem_sync);
-  C.lring = reinterpret_cast<const int16_t*>(w.slice + plan->smem_pring);
+  C.lring = reinterpret_cast<int16_t*>(w.slice + plan->smem_pring);
   C.hsnap = reinterpret_cast<const uint32_t*>(w.slice + plan->smem_hsnap);
   C.pfring = reinterpret_cast<int16_t*>(w.slice + plan->smem_pfring);
   C.arena = w.arena;
@@ -674,7 +762,7 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
       if (J.in_len == 0xFFFFFFFFu) continue;     // the pre-processing stage overflowed its slot: the coder warp reports it
       uint8_t* arena_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.arena, src));
       uint8_t* slice_g = reinterpret_cast<uint8_t*>(__shfl_sync(ZPQ_FULL, (unsigned long long)w.slice, src));
-      init_block_state_role(plan, P.tab, arena_g, slice_g, lane, 1);
+      init_block_state_role(plan, P.tab, arena_g, slice_g, lane, ROLE);
       __syncwarp();
       if (mine) {
         C.in = P.in + J.in_off;
@@ -688,12 +776,20 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
         C.st = 1;
       }
     }
-    // ---- flow control: byte s needs the lead role's byte s (none while the pipeline drains), and the arithmetic
-    //      coder must be done with the ring slots this byte overwrites ----
+    // ---- flow control ----
+    // coder role: byte s needs the lead role's byte s (none while the pipeline drains); whoever reads what this
+    // byte writes (mixer role: ring entries; arithmetic coder: final predictions) must be done with the slots.
+    // mixer role: byte s needs the coder role's byte s; the arithmetic coder must be done with the slots.
     bool run = false;
     if (C.st == 1) {
-      const uint32_t need = C.s + 1 < C.total ? C.s + 1 : C.total;
-      run = C.sync->lpos >= need && C.s <= C.sync->cpos + 6u;
+      if (ROLE == 1) {
+        const uint32_t need = C.s + 1 < C.total ? C.s + 1 : C.total;
+        run = C.sync->lpos >= need;
+        if (DM::SPLIT) run = run && C.s <= C.sync->mpos + 6u;
+        if (!(DM::SPLIT && DM::FINAL_MIX)) run = run && C.s <= C.sync->cpos + 6u;
+      } else {
+        run = C.sync->qfin >= C.s + 1 && C.s <= C.sync->cpos + 6u;
+      }
     }
     if (!__any_sync(ZPQ_FULL, run)) {
       if (__all_sync(ZPQ_FULL, C.st == 3)) break;
@@ -706,39 +802,52 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
     constexpr uint32_t PRO = (D + 7u) / 8u;
     const bool live = C.st == 1;
     const bool steady = run && C.s >= PRO && C.s + 1 < C.total;
-    if (run) { __threadfence_block(); if (gl == 0) C.sync->qpos = C.s; }
+    if (run) { __threadfence_block(); if (gl == 0) { if (ROLE == 1) C.sync->qpos = C.s; else C.sync->mpos = C.s; } }
     __syncwarp();   // the lanes must be CONVERGED when they enter the fast path: its shuffles are whole-warp
     const bool fast = __all_sync(ZPQ_FULL, steady || !live);
     ZPQ_T_IN
     if (fast) {
-      duo_coder_tick<DM, 0, true>(S, C, r, L, H, gl, gmask, gbase, live);
-      duo_coder_tick<DM, 1, true>(S, C, r, L, H, gl, gmask, gbase, live);
-      duo_coder_tick<DM, 2, true>(S, C, r, L, H, gl, gmask, gbase, live);
-      duo_coder_tick<DM, 3, true>(S, C, r, L, H, gl, gmask, gbase, live);
-      duo_coder_tick<DM, 4, true>(S, C, r, L, H, gl, gmask, gbase, live);
-      duo_coder_tick<DM, 5, true>(S, C, r, L, H, gl, gmask, gbase, live);
-      duo_coder_tick<DM, 6, true>(S, C, r, L, H, gl, gmask, gbase, live);
-      duo_coder_tick<DM, 7, true>(S, C, r, L, H, gl, gmask, gbase, live);
+#ifdef ZPQ_DUO_UNROLL
+      if (ROLE == 1) duo_coder_tick<DM, 0, true>(S, C, r, L, H, gl, gmask, gbase, live, 0); else duo_mix_tick<DM, 0, true>(S, C, r, gl, gmask, gbase, live, 0);
+      if (ROLE == 1) duo_coder_tick<DM, 1, true>(S, C, r, L, H, gl, gmask, gbase, live, 1); else duo_mix_tick<DM, 1, true>(S, C, r, gl, gmask, gbase, live, 1);
+      if (ROLE == 1) duo_coder_tick<DM, 2, true>(S, C, r, L, H, gl, gmask, gbase, live, 2); else duo_mix_tick<DM, 2, true>(S, C, r, gl, gmask, gbase, live, 2);
+      if (ROLE == 1) duo_coder_tick<DM, 3, true>(S, C, r, L, H, gl, gmask, gbase, live, 3); else duo_mix_tick<DM, 3, true>(S, C, r, gl, gmask, gbase, live, 3);
+      if (ROLE == 1) duo_coder_tick<DM, 4, true>(S, C, r, L, H, gl, gmask, gbase, live, 4); else duo_mix_tick<DM, 4, true>(S, C, r, gl, gmask, gbase, live, 4);
+      if (ROLE == 1) duo_coder_tick<DM, 5, true>(S, C, r, L, H, gl, gmask, gbase, live, 5); else duo_mix_tick<DM, 5, true>(S, C, r, gl, gmask, gbase, live, 5);
+      if (ROLE == 1) duo_coder_tick<DM, 6, true>(S, C, r, L, H, gl, gmask, gbase, live, 6); else duo_mix_tick<DM, 6, true>(S, C, r, gl, gmask, gbase, live, 6);
+      if (ROLE == 1) duo_coder_tick<DM, 7, true>(S, C, r, L, H, gl, gmask, gbase, live, 7); else duo_mix_tick<DM, 7, true>(S, C, r, gl, gmask, gbase, live, 7);
+#else
+      if (ROLE == 1) {
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) duo_coder_tick<DM, -1, true>(S, C, r, L, H, gl, gmask, gbase, live, k);
+      } else {
+        // the mixer's tick is short and rotates two register pipelines: unrolled, the rotation is free
+        duo_mix_tick<DM, 0, true>(S, C, r, gl, gmask, gbase, live, 0);
+        duo_mix_tick<DM, 1, true>(S, C, r, gl, gmask, gbase, live, 1);
+        duo_mix_tick<DM, 2, true>(S, C, r, gl, gmask, gbase, live, 2);
+        duo_mix_tick<DM, 3, true>(S, C, r, gl, gmask, gbase, live, 3);
+        duo_mix_tick<DM, 4, true>(S, C, r, gl, gmask, gbase, live, 4);
+        duo_mix_tick<DM, 5, true>(S, C, r, gl, gmask, gbase, live, 5);
+        duo_mix_tick<DM, 6, true>(S, C, r, gl, gmask, gbase, live, 6);
+        duo_mix_tick<DM, 7, true>(S, C, r, gl, gmask, gbase, live, 7);
+      }
+#endif
     } else if (run) {
-      duo_coder_tick<DM, 0, false>(S, C, r, L, H, gl, gmask, gbase, true);
-      duo_coder_tick<DM, 1, false>(S, C, r, L, H, gl, gmask, gbase, true);
-      duo_coder_tick<DM, 2, false>(S, C, r, L, H, gl, gmask, gbase, true);
-      duo_coder_tick<DM, 3, false>(S, C, r, L, H, gl, gmask, gbase, true);
-      duo_coder_tick<DM, 4, false>(S, C, r, L, H, gl, gmask, gbase, true);
-      duo_coder_tick<DM, 5, false>(S, C, r, L, H, gl, gmask, gbase, true);
-      duo_coder_tick<DM, 6, false>(S, C, r, L, H, gl, gmask, gbase, true);
-      duo_coder_tick<DM, 7, false>(S, C, r, L, H, gl, gmask, gbase, true);
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) {
+        if (ROLE == 1) duo_coder_tick<DM, -1, false>(S, C, r, L, H, gl, gmask, gbase, true, k); else duo_mix_tick<DM, -1, false>(S, C, r, gl, gmask, gbase, true, k);
+      }
     }
     __syncwarp();
     ZPQ_T_OUT(fast)
     __threadfence_block();
     if (run) {
       ++C.s;
-      if (gl == 0) C.sync->qfin = C.s;
+      if (gl == 0) { if (ROLE == 1) C.sync->qfin = C.s; else C.sync->mfin = C.s; }
       if (C.T >= C.NB + D) C.st = 0;     // every prediction of the block is in the ring
     }
   }
-  ZPQ_T_REPORT("coder")
+  ZPQ_T_REPORT(ROLE == 1 ? "coder" : "mixer")
 }
 
 // ==========================================================================================
@@ -797,7 +906,7 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
         }
       }
     }
-    const bool ready = st == 1 && sync->qfin >= c + CD;
+    const bool ready = st == 1 && ((DM::SPLIT && DM::FINAL_MIX) ? sync->mfin : sync->qfin) >= c + CD;
     if (!__any_sync(ZPQ_FULL, ready)) {
       if (__all_sync(ZPQ_FULL, st == 3)) break;
       __nanosleep(200);
@@ -836,16 +945,20 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
   ZPQ_T_REPORT("arith")
 }
 
-// Kernel body: warp 0 = arithmetic coder of every block of the CTA; warp 1+2p = lead role, warp 2+2p = coder
-// (prediction) role of block group p.
+// Kernel body: warp 0 = arithmetic coder of every block of the CTA; then per block group p: context role, history
+// role, coder (prediction) role and, when the model's MIX components can run on their own, mixer role.
 template <class DM>
 __device__ __forceinline__ void encode_duo_body(const CodecParams& P, uint8_t* smem) {
   Shared S;
   stage_shared(P, smem, S);
+  constexpr int W = DM::SPLIT ? 4 : 3;
   const int warp = threadIdx.x >> 5;
-  if (warp == 0) duo_arith_body<DM>(P, smem, S);
-  else if ((warp - 1) & 1) duo_coder_body<DM>(P, smem, S, (warp - 1) >> 1);
-  else duo_lead_body<DM>(P, smem, S, (warp - 1) >> 1);
+  if (warp == 0) { duo_arith_body<DM>(P, smem, S); return; }
+  const int pair = (warp - 1) / W, role = (warp - 1) % W;
+  if (role == 0) duo_lead_body<DM, 0>(P, smem, S, pair);
+  else if (role == 1) duo_lead_body<DM, 1>(P, smem, S, pair);
+  else if (role == 2) duo_coder_body<DM, 1>(P, smem, S, pair);
+  else duo_coder_body<DM, 2>(P, smem, S, pair);
 }
 
 }  // namespace zpq

@@ -158,7 +158,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   const int nn = std::max(h.n, 1);
   pl.duo_g = duo_g;
   if (duo_g) {
-    pl.smem_sync = stake(32);
+    pl.smem_sync = stake(48);
     pl.smem_pfring = stake(128);
     pl.smem_rows = stake(32u * duo_g);   // duo_g lanes x 16-byte row cache, twice
   } else {
@@ -216,6 +216,21 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         q2 += comp_len(q2[0]);
       }
       pl.duo_hdepth = hdepth; pl.duo_ldepth = ldepth;
+      // the MIX components get a role warp of their own when nothing lane-owned reads a MIX output
+      bool any_mix = false, mix_read = false;
+      q2 = &h.wire[7];
+      for (int i = 0; i < h.n; ++i) {
+        auto rd = [&](int j) { if (j < i && types[j] == C_MIX) mix_read = true; };
+        switch (q2[0]) {
+          case C_AVG: rd(q2[1]); rd(q2[2]); break;
+          case C_MIX2: rd(q2[2]); rd(q2[3]); break;
+          case C_ISSE: case C_SSE: rd(q2[2]); break;
+          case C_MIX: any_mix = true; break;
+          default: break;
+        }
+        q2 += comp_len(q2[0]);
+      }
+      pl.duo_split = duo_g && any_mix && !mix_read;
       pl.duo_ok = duo_g && pl.pipe_ok && h.n <= duo_g && hdepth <= 8;
     }
     if (duo_g) {
@@ -256,15 +271,15 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
       case C_CM:
         limit(29, "max size for CM is 32");
         d.mask = (1u << bits) - 1;
-        d.tab = take(4ull << bits); fill(d.tab, 4ull << bits, 0, 0x80000000u, false);
+        d.tab = take(4ull << bits); fill(d.tab, 4ull << bits, 0, 0x80000000u, false, 3);
         break;
       case C_ICM:
         if (bits > 26) throw Failure(ZPQ_E_CONFIG, "max size for ICM is 26");
         d.mask = (uint32_t)((64ull << bits) - 16);
-        d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false);
-        if (duo_g) {   // the lead role owns ICM maps and addresses them with a 4-byte stride
-          if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 4, 0, true); }
-          else { d.tab2 = take(1024); fill(d.tab2, 1024, 4, 0, false); }
+        d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false, 3);
+        if (duo_g) {   // the history role owns ICM maps and addresses them with a 4-byte stride
+          if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 4, 0, true, 3); }
+          else { d.tab2 = take(1024); fill(d.tab2, 1024, 4, 0, false, 3); }
         } else if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 1, 0, true); }
         else { d.tab2 = take(2048); fill(d.tab2, 2048, 1, 0, false); }
         break;
@@ -295,7 +310,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         const int m = cp[3];
         d.mask = (1u << bits) - 1;
         d.coop = 1;
-        d.tab = take((4ull * m) << bits); fill(d.tab, (4ull * m) << bits, 0, (uint32_t)(65536 / m), false, 1);
+        d.tab = take((4ull * m) << bits); fill(d.tab, (4ull * m) << bits, 0, (uint32_t)(65536 / m), false, pl.duo_split ? 2 : 1);
         for (int j = 0; j < m; ++j) level = std::max(level, 1 + lvl(cp[2] + j));
         break;
       }
@@ -303,7 +318,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         limit(26, "max size for ISSE is 32");
         if (cp[2] >= i) throw Failure(ZPQ_E_CONFIG, "ISSE j >= i");
         d.mask = (uint32_t)((64ull << bits) - 16);
-        d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false);
+        d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false, 3);
         if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 2, 0, true, 1); }
         else { d.tab2 = take(2048); fill(d.tab2, 2048, 2, 0, false, 1); }
         level = 1 + lvl(cp[2]);

@@ -43,7 +43,7 @@ struct InitOp {
   uint32_t value;      // fill word (kind 0) / SSE start count (kind 3)
   uint8_t kind;        // 0 = constant word, 1 = ICM cm template, 2 = ISSE cm template, 3 = SSE pattern, 4 = compact ICM cm (4-byte stride)
   uint8_t to_smem;
-  uint8_t role;        // two-role encoder (zpq_duo.cuh): 0 = table of the lead role, 1 = table of the coder role
+  uint8_t role;        // two-role encoder (zpq_duo.cuh): 0 = table of the context role (HCOMP arrays, MATCH), 3 = of the history role, 1 = of the coder role, 2 = of the mixer role
   uint8_t pad;
 };
 
@@ -100,6 +100,7 @@ struct Plan {
   int32_t duo_ok;               // 1: the two-role encoder applies to this model with this slice layout
   int32_t duo_hdepth;           // deepest look-back into a lane's own prediction history (<= 8)
   int32_t duo_ldepth;           // deepest look-back of a lane-owned consumer (ISSE/AVG/MIX2/SSE)
+  int32_t duo_split;            // 1: the MIX components run in a role warp of their own (no lane-owned component reads a MIX)
   uint32_t smem_sync;           // DuoSync words of the block
   uint32_t smem_pfring;         // int16 [64]: final stretched prediction per bit, for the arithmetic coder warp
   MixDesc mix[kMaxMix];
