@@ -146,135 +146,165 @@ struct LeadCtx {
   }
 };
 
-// End of a byte in a MATCH component (Predictor.cs:382-411).  The index slot was loaded when the byte began
-// (r.t0); the backward verify compares 8 byte pairs per round trip instead of one.
-__device__ __forceinline__ void duo_match_byte(const WarpCtx& W, LaneRegs& r, int y) {
+// ------------------------------------------------------------------------------------------
+// Context role, one byte: HCOMP, the MATCH component for all 8 bits of the byte, and the L2 prefetches.
+// Because the data are known, a MATCH component needs no per-bit work: its predictions for the byte follow from
+// the predicted byte, the match length and the position of the first mispredicted bit (Predictor.cs:273-287),
+// and its end-of-byte update (Predictor.cs:382-411) only needs the bytes coded so far.
+// ------------------------------------------------------------------------------------------
+template <class DM>
+__device__ __forceinline__ void duo_context_byte(const Shared& S, LeadCtx<DM::G>& C, LaneRegs& r, VM& vm, VMEnv& env, int gl,
+                                                  uint32_t gmask, int gbase) {
+  constexpr int G = DM::G;
+  const uint32_t s = C.s;
+  const bool mat = DM::HAS_MATCH && r.type == C_MATCH;
+  const uint32_t byte = C.cb0;
+  C.cb2 = C.fetch(s + 2);
+  r.h = C.hnext;                                              // context of byte s (computed when byte s-1 was here)
+  // ---- MATCH, early part: store the byte, request what the end-of-byte update will look at ----
   uint8_t* buf = r.tab2;
-  buf[r.mpos] = (uint8_t)(W.c8 * 2 + y);
-  r.mpos = (r.mpos + 1) & r.mask2;
-  uint32_t* idx = reinterpret_cast<uint32_t*>(r.tab) + (r.h & r.mask);
-  if (r.ma == 0) {
-    r.mb = r.mpos - (uint32_t)r.t0;
-    if (r.mb & r.mask2) {
-      while (r.ma < 255) {
-        uint32_t a[8], b[8];
+  uint32_t* islot = reinterpret_cast<uint32_t*>(r.tab) + (r.h & r.mask);
+  uint32_t a[8], b[8], npos = 0, cand = 0;
+  if (mat) {
+    buf[r.mpos] = (uint8_t)byte;
+    npos = (r.mpos + 1) & r.mask2;
+    // index slot of this byte's context: requested one byte ago; the previous byte's own update may have hit the same slot
+    cand = islot == reinterpret_cast<uint32_t*>(r.tab) + r.cxt ? r.mb : (uint32_t)r.t0;   // r.cxt / r.mb(hi): slot and value written last
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          a[k] = buf[(r.mpos - r.ma - 1 - k) & r.mask2];
-          b[k] = buf[(r.mpos - r.ma - r.mb - 1 - k) & r.mask2];
-        }
+    for (int k = 0; k < 8; ++k) {       // the 8 most recent bytes and the 8 bytes before the remembered position
+      a[k] = buf[(npos - 1 - k) & r.mask2];
+      b[k] = buf[(cand - 1 - k) & r.mask2];
+    }
+  }
+  // ---- contexts of byte s+1 (HCOMP sees byte s, ZPAQL.cs:1253-1265) and the lines that byte will touch ----
+  if (DM::hcomp(S, C.w, vm, env, byte, gl, gmask)) C.status = BLK_ZPAQL;
+  const uint32_t hn = C.w.H[gl & C.w.hmask];
+  C.hsnap[((s + 1) & 7) * G + gl] = hn;
+  C.hnext = hn;
+  if (r.type == C_ICM || r.type == C_ISSE) {
+    prefetch_l2(r.tab + (((hn + 16u) * 16u) & r.mask));
+    prefetch_l2(r.tab + (((hn + 16u * (16u + (C.cb1 >> 4))) * 16u) & r.mask));
+  }
+  DM::prefetch(r, hn, C.cb1, gl, gmask, gbase);
+  if (mat) {
+    // ---- predictions of the 8 bits (Predictor.cs:273-287) ----
+    const uint32_t len = r.ma;
+    const int d2 = S.dt2k[len & 255u];
+    const int sp0 = S.stretch[d2 & 32767], sp1 = S.stretch[(-d2) & 32767];
+    const uint32_t diff = (r.mbyte ^ byte) & 255u;
+    const int nmatch = diff ? (int)__clz(diff) - 24 : 8;      // bits 0..nmatch-1 are predicted right; bit nmatch (if < 8) ends the match
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int pk = (len && k <= nmatch) ? (((r.mbyte >> (7 - k)) & 1u) ? sp1 : sp0) : 0;
+      C.lring[((s * 8u + k) & (kDuoRing - 1)) * G + gl] = (int16_t)pk;
+    }
+    if (nmatch < 8) r.ma = 0;
+    // ---- end of the byte (Predictor.cs:382-411) ----
+    if (r.ma == 0) {
+      r.c = npos - cand;                                     // r.c: offset of the match (mb)
+      if (r.c & r.mask2) {
         uint32_t n = 0;
         bool go = true;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { go = go && a[k] == b[k] && r.ma + n < 255; n += go ? 1u : 0u; }
-        r.ma += n;
-        if (n < 8) break;
+        for (int k = 0; k < 8; ++k) { go = go && a[k] == b[k]; n += go ? 1u : 0u; }
+        r.ma = n;
+        while (n == 8 && r.ma < 255) {                        // longer than 8: keep comparing, 8 byte pairs per round trip
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a[k] = buf[(npos - r.ma - 1 - k) & r.mask2];
+            b[k] = buf[(npos - r.ma - r.c - 1 - k) & r.mask2];
+          }
+          n = 0; go = true;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { go = go && a[k] == b[k] && r.ma + n < 255; n += go ? 1u : 0u; }
+          r.ma += n;
+        }
       }
-    }
-  } else r.ma += r.ma < 255;
-  *idx = r.mpos;
-  if (r.ma) r.mbyte = buf[(r.mpos - r.mb) & r.mask2];
+    } else r.ma += r.ma < 255;
+    *islot = npos;
+    r.cxt = r.h & r.mask; r.mb = npos;                         // slot and value just written (forwarded to the next byte if it hits the same slot)
+    r.mpos = npos;
+    if (r.ma) r.mbyte = buf[(npos - r.c) & r.mask2];
+    // index slot of the NEXT byte's context: used one byte from now
+    r.t0 = (int)reinterpret_cast<const uint32_t*>(r.tab)[hn & r.mask];
+  }
+  C.cb0 = C.cb1; C.cb1 = C.cb2;
 }
 
-// One bit of a lead role for the lane's component.  K = bit of the byte (0 = most significant).
-// The data-only work is split over two role warps:
-//   LR == 0  context role: HCOMP (contexts of the next byte), the MATCH component, and every L2 prefetch the
-//            contexts allow (hash rows, MATCH index slot, MIX rows) -- it also owns the job queue;
-//   LR == 1  history role: hash-row look-ups and bit histories of ICM/ISSE, the ICM maps, CM and CONS.
-// KC >= 0: the bit index is a compile-time constant (8 specialised copies per byte); KC < 0: it is the run-time
-// argument `krt` and the byte loop stays rolled -- one copy of the code, which is what the instruction caches
-// want when several role warps with different code share an SM (see ZPQ_DUO_UNROLL).
-template <class DM, int KC, int LR>
-__device__ __forceinline__ void duo_lead_tick(const Shared& S, LeadCtx<DM::G>& C, LaneRegs& r, FindAhead& F, uint8_t*& row2,
-                                               VM& vm, VMEnv& env, int gl, uint32_t gmask, int gbase, int krt) {
+// ------------------------------------------------------------------------------------------
+// History role, one nibble: the four bit-history slots a nibble visits are known from the data, so they are read,
+// advanced (StateTable.cs next()) and written back together (Predictor.cs:267-272, 375-381, 440-449); an ICM also
+// predicts and trains its map here, bit by bit because two slots of a nibble may hold the same state.
+// ------------------------------------------------------------------------------------------
+template <class DM>
+__device__ __forceinline__ void duo_history_nibble(const Shared& S, LeadCtx<DM::G>& C, LaneRegs& r, int gl, uint32_t nib, uint32_t bit0,
+                                                    uint32_t hmap_hi) {
   constexpr int G = DM::G;
-  const int K = KC >= 0 ? KC : krt;
-  const bool hashed = LR == 1 && (r.type == C_ICM || r.type == C_ISSE);
-  const uint32_t s = C.s;
-  if (K == 0) {
-    // ---- byte s begins ----
-    C.cb2 = C.fetch(s + 2);
-    r.h = C.hsnap[(s & 7) * G + gl];
-    C.w.c8 = 1; C.w.hmap4 = 1;
-    if (LR == 1) {
-      C.hnext = C.hsnap[((s + 1) & 7) * G + gl];               // written by the context role during its byte s
-      if (hashed) {
-        if (s == 0) lane_find(r, r.h + 16);
-        else find_swap(r, F, row2, r.h + 16);
-        find_issue(r, r.h + 16u * (16u + (C.cb0 >> 4)), F);    // second nibble of this byte
-      }
-    } else {
-      // contexts of byte s+1 (HCOMP sees byte s, ZPAQL.cs:1253-1265) and the lines that byte will touch
-      if (DM::hcomp(S, C.w, vm, env, C.cb0, gl, gmask)) C.status = BLK_ZPAQL;
-      const uint32_t hn = C.w.H[gl & C.w.hmask];
-      C.hsnap[((s + 1) & 7) * G + gl] = hn;
-      C.hnext = hn;
-      if (r.type == C_ICM || r.type == C_ISSE) {
-        prefetch_l2(r.tab + (((hn + 16u) * 16u) & r.mask));
-        prefetch_l2(r.tab + (((hn + 16u * (16u + (C.cb1 >> 4))) * 16u) & r.mask));
-      }
-      if (r.type == C_MATCH) prefetch_l2(reinterpret_cast<const uint32_t*>(r.tab) + (hn & r.mask));
-      DM::prefetch(r, hn, C.cb1, gl, gmask, gbase);
-    }
+  const bool icm = r.type == C_ICM, hashed = icm || r.type == C_ISSE;
+  uint32_t idx[4], bh[4], y[4];
+  y[0] = (nib >> 3) & 1; y[1] = (nib >> 2) & 1; y[2] = (nib >> 1) & 1; y[3] = nib & 1;
+  idx[0] = 1; idx[1] = 2 + y[0]; idx[2] = 4 + y[0] * 2 + y[1]; idx[3] = 8 + y[0] * 4 + y[1] * 2 + y[2];
+  if (DM::HAS_HASHED) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bh[k] = r.row[idx[k]];
+    uint32_t nx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nx[k] = S.ns[bh[k] * 4 + y[k]];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (hashed) r.row[idx[k]] = (uint8_t)nx[k];
   }
-  const int y = (int)((C.cb0 >> (7 - K)) & 1);
-  int val = 0;
-  bool mine = false;
-  if (LR == 1) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int val = 0;
+    bool mine = false;
     if (DM::HAS_HASHED) {
-      // bit history of the slot this bit selects; ICM also predicts and learns here (Predictor.cs:267-272, 375-381).
-      // Straight-line on all lanes: lanes of other types read harmless dummies and store nothing.
-      const bool icm = r.type == C_ICM;
-      const uint32_t si = (uint32_t)C.w.hmap4 & 15u;
-      const uint32_t bh = r.row[si];
-      const uint32_t pn = r.cm[icm ? bh : 0u];
-      const uint32_t nx = S.ns[bh * 4 + y];
+      const uint32_t pn = r.cm[icm ? bh[k] : 0u];
       const int sp = S.stretch[(pn >> 8) & 32767u];
-      if (hashed) r.row[si] = (uint8_t)nx;
-      if (icm) r.cm[bh] = pn + (uint32_t)(((int)(y * 32767 - (int)(pn >> 8))) >> 2);
-      val = icm ? sp : (int)bh;
+      if (icm) r.cm[bh[k]] = pn + (uint32_t)(((int)(y[k] * 32767 - (int)(pn >> 8))) >> 2);
+      val = icm ? sp : (int)bh[k];
       mine = hashed;
     }
     if (DM::HAS_CM) {
       if (r.type == C_CM) {                                    // Predictor.cs:263-266, 365-373
+        C.w.hmap4 = (int)(hmap_hi | idx[k]);
         pa_cm(S, C.w, r);
         val = r.p;
-        up_cm(S, r, y);
+        up_cm(S, r, (int)y[k]);
         mine = true;
       }
     }
     if (DM::HAS_CONS) {
       if (r.type == C_CONS) { val = ((int)r.a1 - 128) * 4; mine = true; }   // Predictor.cs:96-98
     }
-  } else if (DM::HAS_MATCH) {                                  // Predictor.cs:273-287, 382-411
-    const bool mat = r.type == C_MATCH;
-    if (K == 0 && mat) r.t0 = (int)reinterpret_cast<const uint32_t*>(r.tab)[r.h & r.mask];   // index slot of this byte's context, used at K == 7
-    const uint32_t bit = (r.mbyte >> (7 - K)) & 1;
-    const int pm = S.stretch[(S.dt2k[r.ma & 255u] * (1 - 2 * (int)bit)) & 32767];
-    val = r.ma ? pm : 0;
-    if (mat && (int)bit != y) r.ma = 0;
-    if (K == 7 && mat) duo_match_byte(C.w, r, y);
-    mine = mat;
+    if (mine) C.lring[((bit0 + k) & (kDuoRing - 1)) * G + gl] = (int16_t)val;
   }
-  if (mine) C.lring[((s * 8u + K) & (kDuoRing - 1)) * G + gl] = (int16_t)val;
-  // ---- shift the bit into c8 / hmap4 (Predictor.cs:463-474) ----
-  const int c8 = C.w.c8 * 2 + y;
-  if (K == 7) {
-    C.cb0 = C.cb1; C.cb1 = C.cb2;
-  } else if (LR == 1) {
-    if (K == 3) {
-      C.w.hmap4 = (C.w.hmap4 & 0xf) << 5 | y << 4 | 1;
-      if (hashed) {
-        find_resolve(F, row2);                                 // requested when the byte began
-        find_swap(r, F, row2, r.h + 16u * (uint32_t)c8);
-        find_issue(r, C.hnext + 16u, F);                       // first nibble of the next byte
-      }
-    } else {
-      C.w.hmap4 = (C.w.hmap4 & 0x1f0) | (((C.w.hmap4 & 0xf) * 2 + y) & 0xf);
-    }
+}
+
+// History role, one byte: two nibbles, the hash-row look-ups between them (Predictor.cs:550-567).
+template <class DM>
+__device__ __forceinline__ void duo_history_byte(const Shared& S, LeadCtx<DM::G>& C, LaneRegs& r, FindAhead& F, uint8_t*& row2, int gl) {
+  constexpr int G = DM::G;
+  const bool hashed = r.type == C_ICM || r.type == C_ISSE;
+  const uint32_t s = C.s;
+  const uint32_t byte = C.cb0;
+  C.cb2 = C.fetch(s + 2);
+  r.h = C.hsnap[(s & 7) * G + gl];
+  C.hnext = C.hsnap[((s + 1) & 7) * G + gl];                   // written by the context role during its byte s
+  if (hashed) {
+    if (s == 0) lane_find(r, r.h + 16);
+    else find_swap(r, F, row2, r.h + 16);
+    find_issue(r, r.h + 16u * (16u + (byte >> 4)), F);         // second nibble of this byte
   }
-  if (LR == 1 && K == 7 && hashed) find_resolve(F, row2);      // requested at bit 3; swapped in when the next byte begins
-  C.w.c8 = c8;
+  // hmap4 (Predictor.cs:463-474): first nibble = the slot index itself; second nibble = 256 + 16 * high nibble + slot index
+  duo_history_nibble<DM>(S, C, r, gl, byte >> 4, s * 8u, 0u);
+  if (hashed) {
+    find_resolve(F, row2);
+    find_swap(r, F, row2, r.h + 16u * (16u + (byte >> 4)));
+    find_issue(r, C.hnext + 16u, F);                           // first nibble of the next byte
+  }
+  duo_history_nibble<DM>(S, C, r, gl, byte & 15u, s * 8u + 4u, 256u + ((byte >> 4) << 4));
+  if (hashed) find_resolve(F, row2);                           // swapped in when the next byte begins
+  C.cb0 = C.cb1; C.cb1 = C.cb2;
 }
 
 template <class DM, int LR>
@@ -356,6 +386,9 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
           C.w.c8 = 1; C.w.hmap4 = 1;
           vm.b = vm.c = vm.d = vm.f = 0;
           if (gl < G) C.hsnap[gl] = 0;                           // contexts of byte 0 are H == 0
+          C.hnext = 0;
+          r.cxt = 0xFFFFFFFFu;                                    // no index slot written yet
+          r.t0 = 0;                                              // index slot of context 0 in the zeroed table
           C.cb0 = C.fetch(0); C.cb1 = C.fetch(1); C.cb2 = 0;
           C.st = C.total ? 1 : 2;
         }
@@ -412,19 +445,8 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
     ZPQ_T_IN
     if (run) {
       if (LR == 1) __threadfence_block();
-#ifdef ZPQ_DUO_UNROLL
-      duo_lead_tick<DM, 0, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 0);
-      duo_lead_tick<DM, 1, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 1);
-      duo_lead_tick<DM, 2, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 2);
-      duo_lead_tick<DM, 3, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 3);
-      duo_lead_tick<DM, 4, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 4);
-      duo_lead_tick<DM, 5, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 5);
-      duo_lead_tick<DM, 6, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 6);
-      duo_lead_tick<DM, 7, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, 7);
-#else
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) duo_lead_tick<DM, -1, LR>(S, C, r, F, row2, vm, env, gl, gmask, gbase, k);
-#endif
+      if (LR == 0) duo_context_byte<DM>(S, C, r, vm, env, gl, gmask, gbase);
+      else duo_history_byte<DM>(S, C, r, F, row2, gl);
       ++C.s;
     }
     __syncwarp();
