@@ -319,7 +319,8 @@ def main():
                 "traffic": traffic, "kernel": st.kernel.decode(errors="replace"), "kernel_ms": k_ms,
                 "algorithmic_bytes_per_input_byte": ALGO_BYTES_PER_INPUT_BYTE,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "note": "latency-bound: one dependent predict/code/update chain per warp; see DESIGN.md"}
+                "traffic_source": "profiles/traffic.json: DRAM bytes per input byte from an ncu --set full capture of the same kernel, scaled to this launch" if traffic is not None else None,
+                "note": "latency-bound: a dependent chain per role warp and block, 11 blocks per SM is all HBM holds; see DESIGN.md 2.3"}
 
     if rank == 0:
         line = {

@@ -179,3 +179,59 @@ def test_one_call_api(zlib_, oracle):
     arc = zlib_.compressBlock(data, "x0,0c0,0,255i1", "n.txt", "cmt")
     assert arc == oracle.compress_block(data, "x0,0c0,0,255i1", "n.txt", "cmt")
     assert zlib_.decompress(arc + arc) == data + data
+
+
+# ---- the encoder generations must agree byte for byte, and the fast one must be the one that runs ----
+def _encode_with(zlib_, env, data, offs, level=None, method=None):
+    old = {k: os.environ.get(k) for k in ("ZPQ_DUO", "ZPQ_PIPE")}
+    os.environ.update(env)
+    try:
+        with zlib_.Context() as ctx:
+            arc, ooff = (ctx.compress_blocks_level(data, offs, level) if level else ctx.compress_blocks(data, offs, method))
+            return arc.tobytes(), ooff.tolist(), ctx.stats().kernel.decode()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("what", [("level", 1), ("level", 2), ("level", 3), ("method", "x0,0c256,0,255,255"),
+                                  ("method", "x0,4ci1,1,1,1,2awm"), ("method", "x0,0c1,0,255,255a24mm16ts19t0w2")])
+def test_encoder_generations_agree(zlib_, oracle, what):
+    # role-split encoder (zpq_duo.cuh) == time-skewed encoder (zpq_pipe.cuh) == bit-by-bit lane encoder == oracle,
+    # on a ragged batch that makes the blocks of one warp start and finish at different times
+    from tools import synth
+    data = synth.blocks("mixed", 500, 1, 260000).tobytes()
+    cuts = [0, 0, 3, 20000, 20001, 75000, 140000, 141000, 260000]
+    offs = np.asarray(cuts, dtype=np.uint64)
+    kw = {"level": what[1]} if what[0] == "level" else {"method": what[1]}
+    duo, off_d, k_d = _encode_with(zlib_, {"ZPQ_DUO": "1", "ZPQ_PIPE": "1"}, data, offs, **kw)
+    pipe, off_p, k_p = _encode_with(zlib_, {"ZPQ_DUO": "0", "ZPQ_PIPE": "1"}, data, offs, **kw)
+    lanes, off_l, k_l = _encode_with(zlib_, {"ZPQ_DUO": "0", "ZPQ_PIPE": "0"}, data, offs, **kw)
+    assert k_d.startswith("duo/"), k_d          # the role-split kernel really ran
+    assert "time-skewed" in k_p and not k_l.startswith("duo/") and "time-skewed" not in k_l
+    assert duo == pipe == lanes and off_d == off_p == off_l
+    ref = b"".join((oracle.compress_block_level(data[cuts[i]:cuts[i + 1]], what[1]) if what[0] == "level"
+                    else oracle.compress_block(data[cuts[i]:cuts[i + 1]], what[1])) for i in range(len(cuts) - 1))
+    assert duo == ref
+
+
+def test_role_split_encoder_many_blocks_per_sm(gpu_ctx, oracle):
+    # more blocks than one wave of warps holds, so every group takes several jobs from the queue
+    from tools import synth
+    nblk, size = 700, 6000
+    data = synth.blocks("text", 900, nblk, size).tobytes()
+    offs = np.arange(0, nblk * size + 1, size, dtype=np.uint64)
+    gpu_ctx.set_max_resident(64)
+    try:
+        arc, ooff = gpu_ctx.compress_blocks_level(data, offs, 2)
+        assert gpu_ctx.stats().resident_blocks <= 64
+    finally:
+        gpu_ctx.set_max_resident(0)
+    a = arc.tobytes()
+    for i in (0, 1, 63, 64, 65, 333, 698, 699):
+        assert a[int(ooff[i]):int(ooff[i + 1])] == oracle.compress_block_level(data[i * size:(i + 1) * size], 2), i
+    out, _, sha, bst = gpu_ctx.decompress_blocks(arc, ooff)
+    assert out.tobytes() == data and set(sha.tolist()) == {1}
