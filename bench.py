@@ -156,14 +156,14 @@ def run_reference(args):
         vals.append(base["value"])
     v = sum(vals) / len(vals)
     base["value"] = v
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": cfg, "cpu_baseline": base,
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU oracle (C++ restatement of the reference's interpreter semantics; ZPAQSharp is not buildable)",
-    }))
+    })
 
 
 def workload_config(batch_blocks, n_gpus):
@@ -336,11 +336,21 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _emit(obj):
+    """Write the one JSON line to the REAL stdout (libraries such as NCCL print banners to fd 1: it is parked on
+    stderr for the whole run, see the bottom of this file)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: everything else that is written to fd 1 (e.g. "NCCL version ...") goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()

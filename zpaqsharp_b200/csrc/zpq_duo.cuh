@@ -1,32 +1,43 @@
-// zpq_duo.cuh -- two-role block encoder for sm_100a.  NVRTC-safe like zpq_devcore.cuh.
+// zpq_duo.cuh -- role-split block encoder for sm_100a.  NVRTC-safe like zpq_devcore.cuh.
 //
-// The time-skewed encoder of zpq_pipe.cuh still runs every stage of a tick in ONE instruction stream,
-// so a tick costs the SUM of the stage latencies (ncu: 1400 cycles per bit, 18 % issue utilisation),
-// and 24 of the 32 lanes idle for an 8-component model.  This file splits the work where the data
-// dependencies allow it and packs several blocks into a warp:
+// The time-skewed encoder of zpq_pipe.cuh still runs every stage of a tick in ONE instruction stream, so a tick costs
+// the SUM of the stage latencies (ncu: 1400 cycles per bit, 18 % issue utilisation, ~6 cycles per instruction), and 24
+// of the 32 lanes idle for an 8-component model.  HBM caps the blocks in flight (mid.cfg: 11 per SM), so the only way
+// to more throughput is a shorter dependent chain per block and bit.  This file cuts the per-bit work of a block into
+// ROLES, each a warp of its own with a short chain, and packs several blocks into a warp:
 //
-//   lead role  (warp 2p)    everything that depends on the DATA only: HCOMP contexts (ZPAQL.cs:1253-1265),
-//                           hash-row look-ups and bit histories of ICM/ISSE (Predictor.cs:550-567, 375-381),
-//                           and the complete CONS / CM / ICM / MATCH components -- their predictions never
-//                           read another prediction (Predictor.cs:263-287, 365-411).
-//   coder role (warp 2p+1)  everything that depends on PREDICTIONS: ISSE weights, AVG, MIX2, SSE, MIX
-//                           (Predictor.cs:288-340, 414-455) and the arithmetic coder (Encoder.cs:87-103),
-//                           time-skewed by component delay as in zpq_pipe.cuh.
+//   context role   everything per BYTE that depends on the data only: HCOMP contexts (ZPAQL.cs:1253-1265), the MATCH
+//                  component for all 8 bits of the byte at once (Predictor.cs:273-287, 382-411), L2 prefetch of every
+//                  table line the next byte will touch; it owns the job queue.
+//   history role   hash-row look-ups and bit histories of ICM/ISSE, nibble by nibble (Predictor.cs:550-567, 375-381),
+//                  and the complete ICM / CM / CONS components -- their predictions never read another prediction
+//                  (Predictor.cs:263-272, 365-373).
+//   coder role     what depends on PREDICTIONS and is owned by one lane: ISSE weights, AVG, MIX2, SSE
+//                  (Predictor.cs:288-340, 414-455), time-skewed by component delay as in zpq_pipe.cuh; predictions travel
+//                  between lanes by SHFL from a per-lane history of the last 8 bits kept in registers, so a tick has no
+//                  shared-memory read-after-write.
+//   mixer role     every MIX (Predictor.cs:302-316, 427-439), when nothing lane-owned reads a MIX output (DM::SPLIT;
+//                  otherwise the coder role evaluates the MIXes too): weight rows requested kDuoMixAhead bits ahead in
+//                  a register pipeline, trained rows forwarded when a row repeats.
+//   arithmetic coder  ONE warp per CTA, lane b codes block b of the CTA (Encoder.cs:39-103).
 //
-// The lead role hands one int16 per component and bit (a stretched prediction, or the bit history an
-// ISSE will index its weights with) to the coder role through a 64-bit-deep ring in shared memory,
-// plus the HCOMP contexts of the last 8 bytes; flow control is two byte counters per block.
-// Inside the coder role predictions travel between lanes by SHFL from a per-lane history of the last
-// 8 bits kept in registers, so a tick has no shared-memory read-after-write at all and its stages
-// (ISSE chain link, MIX dot product, coder) are independent instruction chains.
+// The two lead roles hand one int16 per component and bit (a stretched prediction, or the bit history an ISSE will
+// index its weights with) to the coder / mixer roles through a 64-bit-deep ring in shared memory, plus the HCOMP
+// contexts of the last 8 bytes; the coder role replaces an entry by its own prediction once it has used it (the mixer
+// reads that); the last component's prediction goes to a third ring for the arithmetic coder.  Flow control is one
+// byte counter per role and block (DuoSync): a producer stays at most 6 bytes ahead of the last reader of its ring.
 //
-// A warp serves 32/G blocks at once (G = 8, 16 or 32 lanes per block, the model's component count
-// rounded up): lanes [g*G, g*G+G) of the lead warp and of the coder warp own block g of the pair.
-// Groups run in lockstep while they have work; a group that waits (ring full / ring empty / no job)
-// sits the byte out under a branch, every collective uses the group's own member mask.
+// A role warp serves 32/G blocks at once (G = 8, 16 or 32 lanes per block, the model's component count rounded up):
+// lanes [g*G, g*G+G) of every role warp of a group own block g of the group.  Groups run in lockstep while they have
+// work; a group that waits (ring full / ring empty / no job) sits the byte out under a branch, every collective uses
+// the group's own member mask; a fast path without range tests and with whole-warp collectives runs whenever every
+// group is in its steady state.
 //
-// The arithmetic is exactly the reference's, per component in the same order, bit for bit; only the
-// interleaving between components and blocks changes.  Decoding cannot be split this way.
+// Five instruction streams share an SM, so code size matters: with every byte loop unrolled the kernel ran 1.5x
+// slower on most SMs (instruction fetch); the loops are rolled except the mixer's (see ZPQ_DUO_UNROLL).
+//
+// The arithmetic is exactly the reference's, per component in the same order, bit for bit; only the interleaving
+// between components and blocks changes.  Decoding cannot be split this way.
 #pragma once
 #include "zpq_pipe.cuh"
 
