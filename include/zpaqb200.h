@@ -94,6 +94,16 @@ double zpq_block_memory(const uint8_t* hdr, uint64_t hdr_len);
  * scheduler divides free HBM by.  Negative on error. */
 int64_t zpq_device_state_bytes(const uint8_t* hdr, uint64_t hdr_len, int for_decode);
 
+/* How the role-split encoder (zpq_duo.cuh) would run this model with `smem_bytes` of shared memory per SM and
+ * `blocks_per_sm` resident blocks wanted: the device analogue of asking the reference whether its x86 JIT applies
+ * (Predictor.assemble_p, Predictor.cs:579-1356).  Host only, no device needed.  out[0..7] =
+ *   [0] 1 if the role-split encoder applies, else 0 (the single-warp encoders are used)
+ *   [1] lanes per block in a role warp (8, 16 or 32)          [2] role warps per block group (3 or 4)
+ *   [3] blocks per SM that fit (<= blocks_per_sm)              [4] shared-memory bytes per resident block
+ *   [5] coder delay in bits (Plan::coder_delay)                [6] 1 if the MIX components get a warp of their own
+ *   [7] warps per CTA.                                          Returns 0 or a negative error code. */
+int zpq_encoder_plan(const uint8_t* hdr, uint64_t hdr_len, uint32_t smem_bytes, uint32_t blocks_per_sm, int32_t* out8);
+
 /* ---- compression --------------------------------------------------------------------------- */
 
 /* LibZPAQ.compressBlock(in, out, method, filename, comment, dosha1), LibZPAQ.cs:117-325, for nb

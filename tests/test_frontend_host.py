@@ -112,3 +112,23 @@ def test_context_creation_fails_loudly_without_gpu(zlib_):
     with pytest.raises(zlib_.ZpaqError) as e:
         zlib_.Context()
     assert "CUDA" in str(e.value)
+
+
+def test_role_split_encoder_plan_for_builtin_models(zlib_):
+    # host logic of the role-split encoder (zpq_duo.cuh) without a device: which models it takes, lanes per block,
+    # role warps per group, and that mid.cfg fits its 11 resident blocks per SM into the 227 KB an SM has
+    B200_SMEM = 232448
+    mid = zlib_.encoder_plan(zlib_.builtin_model(2), B200_SMEM, 11)
+    assert mid["applies"] == 1 and mid["lanes_per_block"] == 8 and mid["mixer_role"] == 1 and mid["roles"] == 4
+    assert mid["blocks_per_sm"] == 11 and mid["warps_per_cta"] == 1 + 4 * 3 and mid["coder_delay"] == 7
+    assert 11 * mid["smem_per_block"] + 81 * 1024 <= B200_SMEM
+    mn = zlib_.encoder_plan(zlib_.builtin_model(1), B200_SMEM, 32)
+    assert mn["applies"] == 1 and mn["lanes_per_block"] == 8 and mn["mixer_role"] == 0 and mn["roles"] == 3
+    assert mn["blocks_per_sm"] == 20          # 15 role warps / 3 roles = 5 groups of 4 blocks
+    mx = zlib_.encoder_plan(zlib_.builtin_model(3), B200_SMEM, 5)
+    assert mx["applies"] == 1 and mx["lanes_per_block"] == 32 and mx["mixer_role"] == 0   # MIX2/SSE read the MIX outputs
+    assert mx["blocks_per_sm"] == 5 and mx["warps_per_cta"] == 16
+    # a model with more than 32 components is left to the step-scheduled kernels
+    hdr, _ = zlib_.compile_config(zlib_.make_config("x0,0" + "c0,0,255" * 40)[0], [0] * 9) if hasattr(zlib_, "compile_config") else (None, None)
+    if hdr:
+        assert zlib_.encoder_plan(hdr)["applies"] == 0

@@ -966,6 +966,32 @@ int64_t zpq_device_state_bytes(const uint8_t* hdr, uint64_t hdr_len, int for_dec
   return rc ? rc : v;
 }
 
+int zpq_encoder_plan(const uint8_t* hdr, uint64_t hdr_len, uint32_t smem_bytes, uint32_t blocks_per_sm, int32_t* out8) {
+  if (!hdr || !out8) return ZPQ_E_ARG;
+  return guarded(nullptr, [&]() {
+    Header h; parse_header(hdr, hdr_len, h);
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (h.n < 1 || h.n > 32) return;
+    const uint32_t G = h.n <= 8 ? 8u : h.n <= 16 ? 16u : 32u, B = 32 / G;
+    std::unique_ptr<Plan> p(new Plan);
+    build_plan(h, false, 48 * 1024, *p, (int)G);
+    const uint32_t roles = p->duo_split ? 4u : 3u;
+    uint32_t wb = std::min(std::max(blocks_per_sm, 1u), std::min((15u / roles) * B, 32u));
+    bool ok = false;
+    for (; wb >= 1 && !ok; --wb) {
+      SmemLayout L;
+      const uint32_t common = common_smem(*p, L);
+      const uint32_t avail = smem_bytes > common ? smem_bytes - common : 0;
+      build_plan(h, false, (avail / wb) & ~127u, *p, (int)G);
+      ok = p->duo_ok && p->pipe_maps && (uint64_t)wb * p->smem_warp_bytes <= avail;
+      if (ok) break;
+    }
+    out8[0] = ok ? 1 : 0; out8[1] = (int32_t)G; out8[2] = (int32_t)roles; out8[3] = ok ? (int32_t)wb : 0;
+    out8[4] = (int32_t)p->smem_warp_bytes; out8[5] = p->coder_delay; out8[6] = p->duo_split;
+    out8[7] = ok ? (int32_t)(1 + roles * ((wb + B - 1) / B)) : 0;
+  });
+}
+
 int zpq_compress_blocks_model(zpq_ctx* ctx, const uint8_t* hdr, uint64_t hdr_len, const uint8_t* pcomp, uint64_t pcomp_len,
                               const int* args9, const uint8_t* in, const uint64_t* in_off, uint32_t nb,
                               const char* filename0, const char* comment0, int dosha1, int with_tag, uint8_t* out,

@@ -978,16 +978,18 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
   ZPQ_T_REPORT("arith")
 }
 
-// Kernel body: warp 0 = arithmetic coder of every block of the CTA; then per block group p: context role, history
-// role, coder (prediction) role and, when the model's MIX components can run on their own, mixer role.
+// Kernel body.  Per block group p: context role, history role, coder (prediction) role and, when the model's MIX
+// components can run on their own, mixer role -- warp 4p+r, so role r of every group lands on SM sub-partition r and
+// shares its instruction cache with copies of itself; the LAST warp is the arithmetic coder of every block of the CTA
+// (it joins the context roles' sub-partition, the lightest).
 template <class DM>
 __device__ __forceinline__ void encode_duo_body(const CodecParams& P, uint8_t* smem) {
   Shared S;
   stage_shared(P, smem, S);
   constexpr int W = DM::SPLIT ? 4 : 3;
-  const int warp = threadIdx.x >> 5;
-  if (warp == 0) { duo_arith_body<DM>(P, smem, S); return; }
-  const int pair = (warp - 1) / W, role = (warp - 1) % W;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (warp == nwarps - 1) { duo_arith_body<DM>(P, smem, S); return; }
+  const int pair = warp / W, role = warp % W;
   if (role == 0) duo_lead_body<DM, 0>(P, smem, S, pair);
   else if (role == 1) duo_lead_body<DM, 1>(P, smem, S, pair);
   else if (role == 2) duo_coder_body<DM, 1>(P, smem, S, pair);

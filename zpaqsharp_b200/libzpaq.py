@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "zpq_make_config", "zpq_expand_method", "zpq_compile_config", "zpq_builtin_model", "zpq_block_memory",
     "zpq_device_state_bytes", "zpq_compress_blocks", "zpq_compress_blocks_level", "zpq_compress_blocks_model",
     "zpq_compress_blocks_model_dev", "zpq_find_blocks", "zpq_decompress_blocks", "zpq_decompressed_bound",
-    "zpq_get_stats", "zpq_version", "zpq_specialize_model",
+    "zpq_get_stats", "zpq_version", "zpq_specialize_model", "zpq_encoder_plan",
 ]
 
 
@@ -166,6 +166,19 @@ def block_memory(hdr: bytes) -> float:
 
 def device_state_bytes(hdr: bytes, for_decode: bool = False) -> int:
     return load().zpq_device_state_bytes(hdr, len(hdr), 1 if for_decode else 0)
+
+
+def encoder_plan(hdr: bytes, smem_bytes: int = 232448, blocks_per_sm: int = 32) -> dict:
+    """How the role-split encoder would run this model (host only): see zpq_encoder_plan in include/zpaqb200.h."""
+    out = (C.c_int32 * 8)()
+    L = load()
+    L.zpq_encoder_plan.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]
+    L.zpq_encoder_plan.restype = C.c_int
+    rc = L.zpq_encoder_plan(hdr, len(hdr), smem_bytes, blocks_per_sm, out)
+    if rc:
+        raise ZpaqError(rc, "zpq_encoder_plan failed")
+    keys = ["applies", "lanes_per_block", "roles", "blocks_per_sm", "smem_per_block", "coder_delay", "mixer_role", "warps_per_cta"]
+    return dict(zip(keys, [int(v) for v in out]))
 
 
 def specialize_model(hdr: bytes):
