@@ -148,9 +148,9 @@ struct LeadCtx {
   int16_t* lring;            // [bit & 63][G]
   uint32_t* hsnap;           // [byte & 7][G]
   const uint8_t* in; const uint8_t* preamble;
-  uint32_t pre_len, total, s, seq, status;
+  uint32_t pre_len, total, s, seq, status, job;
   uint32_t cb0, cb1, cb2, hnext;
-  int st;                    // 0 idle, 1 running, 2 all bytes done (waiting for the coder role), 3 retired
+  int st;                    // 0 idle, 1 running, 2 all bytes done (waiting for the arithmetic coder), 3 retired
   __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
     if (i < pre_len) return preamble[i];
     return i < total ? in[i - pre_len] : 0u;
@@ -343,7 +343,7 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
   C.lring = reinterpret_cast<int16_t*>(w.slice + plan->smem_pring);
   C.hsnap = reinterpret_cast<uint32_t*>(w.slice + plan->smem_hsnap);
   C.preamble = P.preamble;
-  C.in = P.in; C.pre_len = 0; C.total = 0; C.s = 0; C.seq = 0; C.status = BLK_OK;
+  C.in = P.in; C.pre_len = 0; C.total = 0; C.s = 0; C.seq = 0; C.status = BLK_OK; C.job = 0;
   C.cb0 = C.cb1 = C.cb2 = 0; C.hnext = 0;
   C.st = valid ? 0 : 3;
   C.w.arena = w.arena; C.w.H = w.H; C.w.hmask = w.hmask; C.w.c8 = 1; C.w.hmap4 = 1;
@@ -416,15 +416,14 @@ __device__ __forceinline__ void duo_lead_body(const CodecParams& P, uint8_t* sme
       if (C.st == 0 && C.sync->jobseq != C.seq) {
         __threadfence_block();
         C.seq += 1;
-        const uint32_t job = C.sync->jobid;
-        C.status = job;            // (the job index, until the group has been set up)
-        if (job == kDuoRetire) C.st = 3; else fresh = true;
+        C.job = C.sync->jobid;
+        if (C.job == kDuoRetire) C.st = 3; else fresh = true;
       }
       uint32_t want = __ballot_sync(ZPQ_FULL, fresh && gl == 0);
       while (want) {
         const int src = __ffs(want) - 1;
         want &= want - 1;
-        const uint32_t job = __shfl_sync(ZPQ_FULL, C.status, src);
+        const uint32_t job = __shfl_sync(ZPQ_FULL, C.job, src);
         const EncJob J = P.ejobs[job];
         const bool mine = gbase == src;
         if (J.in_len == 0xFFFFFFFFu) continue;     // the pre-processing stage overflowed its slot: nothing to do
