@@ -104,8 +104,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _reference_block_coder():
+    """The reference's own text for the hot loop, when oracle/_ref holds it: Predictor.init / predict0 / update0 / find,
+    ZPAQL.execute and Encoder.encode compiled by oracle/build_ref.py (prebuilt; nothing is read from /root/reference at
+    run time).  Returns code(block) -> coded bytes of the block, or None."""
+    import ctypes as C
+    import hashlib
+    try:
+        from oracle import build_ref, frontend
+        path = build_ref.build_predictor()
+        if not path or not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        kat = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kat.json")))
+        tabs = [np.asarray(kat["sdt2k"], dtype=np.int32), np.asarray(kat["sdt"], dtype=np.int32), np.asarray(kat["ssquasht"], dtype=np.uint16),
+                np.asarray(kat["stdt"], dtype=np.int32), np.asarray(kat["sns"], dtype=np.uint8)]
+        L.ref_predictor_tables.argtypes = [C.c_void_p] * 5
+        L.ref_predictor_tables(*[t.ctypes.data for t in tabs])
+        L.ref_code_block.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong]
+        L.ref_code_block.restype = C.c_longlong
+        hdr = bytes(frontend.builtin_model(LEVEL)[0])
+    except Exception:
+        return None
+
+    def code(b):
+        hashlib.sha1(b).digest()                    # compressBlock hashes the block first (LibZPAQ.cs:143-155; the SHA1 class itself is missing)
+        cap = len(b) + len(b) // 4 + 4096
+        out = C.create_string_buffer(cap)
+        n = L.ref_code_block(hdr, len(hdr), b"\x00", 1, b, len(b), out, cap)      # ctypes releases the GIL: one block per thread
+        if n < 0:
+            raise RuntimeError("reference coder failed")
+        return out.raw[:n]
+    return code
+
+
 def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
-    """Time the CPU oracle (one block per host thread) on a bounded sample of the workload."""
+    """Time the CPU path (one block per host thread) on a bounded sample of the workload: the reference's own text for the
+    per-bit hot loop when oracle/_ref holds it (kind "reference"), else the oracle port (kind "port")."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po
     from tools import synth
@@ -113,6 +148,7 @@ def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
     cores = os.cpu_count() or 1
     data = synth.blocks("mixed", 0, cores, BLOCK)
     blocks = [data[i * BLOCK:(i + 1) * BLOCK].tobytes() for i in range(cores)]
+    ref_code = _reference_block_coder()
 
     def comp(b):
         return po.compress_block_level(b, LEVEL)
@@ -120,26 +156,38 @@ def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
         arcs = list(ex.map(comp, blocks))
-    t_c = time.perf_counter() - t0
-    out = {"value": cores * BLOCK / 1e6 / t_c, "unit": "MB/s", "cores": cores, "kind": "port",
+    t_port = time.perf_counter() - t0
+    out = {"value": cores * BLOCK / 1e6 / t_port, "unit": "MB/s", "cores": cores, "kind": "port",
            "sample": "%d blocks of %d B (one per host thread), mid.cfg, oracle C++ -O2" % (cores, BLOCK),
-           "seconds": t_c}
-    if decompress and t_c < seconds_budget:
+           "seconds": t_port}
+    if ref_code is not None:
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            coded = list(ex.map(ref_code, blocks))
+        t_ref = time.perf_counter() - t0
+        # the reference text must have produced the coded payload of the oracle's archive block (13-byte tag, zPQ header,
+        # segment header in front; 00 00 00 00 FD sha1[20] FF behind)
+        assert all(a[-26 - len(c):-26] == c for a, c in zip(arcs, coded)), "reference text and oracle disagree"
+        out.update({"value": cores * BLOCK / 1e6 / t_ref, "kind": "reference", "seconds": t_ref, "port_value": cores * BLOCK / 1e6 / t_port,
+                    "sample": "%d blocks of %d B (one per host thread), mid.cfg; the reference's own Predictor.init/predict0/update0/find, "
+                              "ZPAQL.execute and Encoder.encode text compiled -O2 from /root/reference by oracle/build_ref.py "
+                              "(+ SHA-1 of the block); coded bytes checked against the oracle's archives" % (cores, BLOCK)})
+    if decompress and out["seconds"] < seconds_budget:
         t0 = time.perf_counter()
         with ThreadPoolExecutor(cores) as ex:
             back = list(ex.map(lambda a: po.decompress(a, cap=BLOCK + 64)[0], arcs))
         t_d = time.perf_counter() - t0
         assert all(b == s for b, s in zip(back, blocks))
-        out["decompress_value"] = cores * BLOCK / 1e6 / t_d
+        out["decompress_value"] = cores * BLOCK / 1e6 / t_d        # (oracle port: the reference's Decoder loop is not assembled)
     t0 = time.perf_counter()
-    comp(blocks[0])
+    (ref_code or comp)(blocks[0])
     out["single_core_value"] = BLOCK / 1e6 / (time.perf_counter() - t0)
     return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
-    reference does not compile, so this is the oracle port; rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores, rank 0 only: the reference's own
+    text for the per-bit hot loop compiled into oracle/_ref (kind "reference"), or the oracle port when that is missing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -162,7 +210,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": cfg, "cpu_baseline": base,
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU oracle (C++ restatement of the reference's interpreter semantics; ZPAQSharp is not buildable)",
+        "note": "kind reference: Predictor/ZPAQL/Encoder text of the reference compiled from /root/reference (oracle/build_ref.py); "
+                "kind port: the C++ oracle restating it (ZPAQSharp as a whole is not buildable)",
     })
 
 

@@ -343,6 +343,7 @@ PRED_OUT = os.path.join(OUT_DIR, "libpredictor_ref.so")
 
 def predictor_text() -> str:
     exe = _method_text(ZPAQL_SRC, "int execute()")
+    enc = _method_text(ENC_SRC, "void encode(int y, int p)")
     fix = lambda t: re.sub(r"Array\.Resize\(ref\s+([\w\.]+),\s*", r"\1.resize(", t).replace(".Length", ".size()").replace("@", "")
     init = fix(_method_text(PRED_SRC, "void init() // build model"))
     pred = fix(_method_text(PRED_SRC, "int predict0() // default"))
@@ -418,6 +419,18 @@ struct RefPredictor {
   // ---- reference text ----
 """ + find + "\n" + init + "\n" + pred + "\n" + upd + r"""
 };
+struct RefSink { unsigned char* p; unsigned long long cap, n; void put(int c) { if (n < cap) p[n] = (unsigned char)c; ++n; } };
+struct RefBlockEncoder {          // Encoder (Encoder.cs:26-103) around the reference predictor: encode() is reference text
+  uint low, high; RefSink out; RefPredictor* pr;
+""" + enc + r"""
+  void compress(int c) {          // Encoder.compress, Encoder.cs:39-57 (modeled branch)
+    if (c == -1) encode(1, 0);
+    else {
+      encode(0, 0);
+      for (int i = 7; i >= 0; --i) { int p = pr->predict0() * 2 + 1; int y = c >> i & 1; encode(y, p); pr->update0(y); }
+    }
+  }
+};
 extern "C" void ref_predictor_tables(const int* a_sdt2k, const int* a_sdt, const unsigned short* a_ssquasht, const int* a_stdt, const unsigned char* a_sns) {
   memcpy(sdt2k, a_sdt2k, sizeof sdt2k); memcpy(sdt, a_sdt, sizeof sdt); memcpy(ssquasht, a_ssquasht, sizeof ssquasht);
   memcpy(stdt, a_stdt, sizeof stdt); memcpy(sns, a_sns, sizeof sns);
@@ -444,6 +457,30 @@ extern "C" long long ref_predict_trace(const unsigned char* hdr, unsigned long l
       for (int b = 7; b >= 0; --b) { probs[k++] = (unsigned short)(P->predict0() * 2 + 1); P->update0(input[i] >> b & 1); }
     delete P;
     return (long long)k;
+  } catch (const std::exception&) { return -1; }
+}
+// The coded stream of one block as Compressor.compress produces it (Compressor.cs:156-221, 224-232): `preamble` (the
+// PCOMP bytes, Compressor.cs:177-188) and the data go through Encoder.compress, then EOS.  Returns coded bytes or -1.
+extern "C" long long ref_code_block(const unsigned char* hdr, unsigned long long hlen, const unsigned char* preamble, unsigned long long npre,
+                                    const unsigned char* input, unsigned long long n, unsigned char* out, unsigned long long cap) {
+  try {
+    RefPredictor* P = new RefPredictor();
+    P->initTables = false; P->pcode = 0; P->pcode_size = 0; P->c8 = 1; P->hmap4 = 1;
+    int ncomp = hdr[6], pos = 7;
+    for (int i = 0; i < ncomp; ++i) pos += compsize[hdr[pos]];
+    int cend = pos + 1, hlen2 = (int)hlen - cend;
+    RefVM& z = P->z;
+    z.cend = cend; z.hbegin = cend + 128; z.hend = z.hbegin + hlen2 - 1;
+    z.header.resize(z.hend + 304);
+    memcpy(&z.header[0], hdr, cend);
+    memcpy(&z.header[z.hbegin], hdr + cend, hlen2);
+    P->init();
+    RefBlockEncoder e; e.low = 1; e.high = 0xFFFFFFFFu; e.out.p = out; e.out.cap = cap; e.out.n = 0; e.pr = P;
+    for (unsigned long long i = 0; i < npre; ++i) e.compress(preamble[i]);
+    for (unsigned long long i = 0; i < n; ++i) e.compress(input[i]);
+    e.compress(-1);
+    delete P;
+    return (long long)e.out.n;
   } catch (const std::exception&) { return -1; }
 }
 """

@@ -61,3 +61,26 @@ def test_every_bit_probability_matches_reference_predictor(ref, what):
     got = po.predict_trace(hdr, data)
     bad = np.nonzero(got != want)[0]
     assert bad.size == 0, "first differing bit %d of %d: oracle %d, reference %d" % (bad[0], n, got[bad[0]], want[bad[0]])
+
+
+def _coded_payload(archive: bytes, hdr: bytes, filename: bytes = b"", comment: bytes = b"") -> bytes:
+    """The coded bytes of a one-segment archive block: between the segment header and `00 00 00 00 FD sha1 FF`."""
+    prefix = 13 + 5 + len(hdr) + 1 + len(filename) + 1 + len(comment) + 1 + 1
+    assert archive[-1] == 255 and archive[-22] == 253 and archive[-26:-22] == b"\x00\x00\x00\x00"
+    return archive[prefix:-26]
+
+
+@pytest.mark.parametrize("level", [1, 2, 3])
+def test_coded_bytes_match_reference_predictor_and_coder(ref, level):
+    # reference predictor text x reference Encoder.encode text == the coded payload of the oracle's archive block
+    ref.ref_code_block.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong]
+    ref.ref_code_block.restype = C.c_longlong
+    hdr, _ = frontend.builtin_model(level)
+    hdr = bytes(hdr)
+    data = synth.blocks("mixed", 400 + level, 1, 50000).tobytes()
+    arc = po.compress_block_level(data, level)
+    want = _coded_payload(arc, hdr, b"", str(len(data)).encode())
+    cap = len(data) * 2 + 4096
+    out = C.create_string_buffer(cap)
+    n = ref.ref_code_block(hdr, len(hdr), b"\x00", 1, data, len(data), out, cap)      # preamble 0: no PCOMP (Compressor.cs:188)
+    assert n == len(want) and out.raw[:n] == want
