@@ -38,6 +38,8 @@ namespace ZPAQSharp
             byte* hdr, ulong hdrCap, out ulong hdrLen, byte* pcomp, ulong pcompCap, out ulong pcompLen);
         [DllImport(Lib)] public static extern long zpq_builtin_model(int level, byte* hdr, ulong hdrCap);
         [DllImport(Lib)] public static extern double zpq_block_memory(byte* hdr, ulong hdrLen);
+        [DllImport(Lib)] public static extern long zpq_device_state_bytes(byte* hdr, ulong hdrLen, int forDecode);
+        [DllImport(Lib)] public static extern int zpq_encoder_plan(byte* hdr, ulong hdrLen, uint smemBytes, uint blocksPerSm, int* out8);
     }
 
     /// <summary>GPU-backed bodies for the LibZPAQ entry points of the compress/decompress path.</summary>
