@@ -342,14 +342,14 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   const bool duo = ok && pd.duo_ok;
   if (duo_g) *duo_g = duo ? G : 0;
   if (duo) {
-    uint32_t lmask = tmask[C_CONS] | tmask[C_CM] | tmask[C_ICM] | tmask[C_MATCH];
+    uint32_t lmask = tmask[C_CONS] | tmask[C_CM] | tmask[C_MATCH];   // components the lead roles predict completely
     o << "struct Duo_" << name << " {\n"
       << "  static constexpr int G = " << G << ", N = " << pl.n << ", D = " << pd.coder_delay << ", LDEPTH = " << pd.duo_ldepth
       << ", HDEPTH = " << pd.duo_hdepth << ";\n"
       << "  static constexpr unsigned LMASK = 0x" << std::hex << lmask << std::dec << "u;\n"
       << "  static constexpr bool HAS_HASHED = " << ((tmask[C_ICM] | tmask[C_ISSE]) ? "true" : "false") << ", HAS_MATCH = " << (tmask[C_MATCH] ? "true" : "false")
       << ", HAS_CM = " << (tmask[C_CM] ? "true" : "false") << ", HAS_CONS = " << (tmask[C_CONS] ? "true" : "false")
-      << ", HAS_ISSE = " << (tmask[C_ISSE] ? "true" : "false") << ", NEEDK = " << ((tmask[C_AVG] | tmask[C_MIX2]) ? "true" : "false")
+      << ", HAS_ISSE = " << ((tmask[C_ISSE] | tmask[C_ICM]) ? "true" : "false") << ", NEEDK = " << ((tmask[C_AVG] | tmask[C_MIX2]) ? "true" : "false")
       << ", FINAL_MIX = " << (pl.comp[pl.n - 1].type == C_MIX ? "true" : "false") << ", SPLIT = " << (pd.duo_split ? "true" : "false") << ";\n";
     for (int k = 0; k < pl.nmix; ++k)
       if (mix_regs)

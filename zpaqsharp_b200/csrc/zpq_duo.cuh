@@ -76,7 +76,9 @@ constexpr uint32_t kDuoRing = 64;     // bits of lead-role output kept per block
 constexpr uint32_t kDuoRetire = 0xFFFFFFFFu;
 
 // table initialisation of one role (Predictor.cs:96-165), by all 32 lanes of the calling warp
-__device__ __forceinline__ void init_block_state_role(const Plan* plan, const Tables* tab, uint8_t* arena, uint8_t* slice, int lane, int role) {
+// Out of line on purpose: inlined into the four role bodies it put 4 x 7.5 KB of cold code between their hot loops and
+// the kernel ran 10-20 % slower (instruction cache); it runs once per block and role.
+static __device__ __noinline__ void init_block_state_role(const Plan* plan, const Tables* tab, uint8_t* arena, uint8_t* slice, int lane, int role) {
   const int nops = plan->ninit;
   for (int k = 0; k < nops; ++k) {
     const InitOp op = plan->init[k];
@@ -244,14 +246,14 @@ __device__ __forceinline__ void duo_context_byte(const Shared& S, LeadCtx<DM::G>
 
 // ------------------------------------------------------------------------------------------
 // History role, one nibble: the four bit-history slots a nibble visits are known from the data, so they are read,
-// advanced (StateTable.cs next()) and written back together (Predictor.cs:267-272, 375-381, 440-449); an ICM also
-// predicts and trains its map here, bit by bit because two slots of a nibble may hold the same state.
+// advanced (StateTable.cs next()) and written back together (Predictor.cs:267-272, 375-381, 440-449); the maps indexed
+// by these states belong to the coder role.
 // ------------------------------------------------------------------------------------------
 template <class DM>
 __device__ __forceinline__ void duo_history_nibble(const Shared& S, LeadCtx<DM::G>& C, LaneRegs& r, int gl, uint32_t nib, uint32_t bit0,
                                                     uint32_t hmap_hi) {
   constexpr int G = DM::G;
-  const bool icm = r.type == C_ICM, hashed = icm || r.type == C_ISSE;
+  const bool hashed = r.type == C_ICM || r.type == C_ISSE;
   uint32_t idx[4], bh[4], y[4];
   y[0] = (nib >> 3) & 1; y[1] = (nib >> 2) & 1; y[2] = (nib >> 1) & 1; y[3] = nib & 1;
   idx[0] = 1; idx[1] = 2 + y[0]; idx[2] = 4 + y[0] * 2 + y[1]; idx[3] = 8 + y[0] * 4 + y[1] * 2 + y[2];
@@ -268,13 +270,7 @@ __device__ __forceinline__ void duo_history_nibble(const Shared& S, LeadCtx<DM::
   for (int k = 0; k < 4; ++k) {
     int val = 0;
     bool mine = false;
-    if (DM::HAS_HASHED) {
-      const uint32_t pn = r.cm[icm ? bh[k] : 0u];
-      const int sp = S.stretch[(pn >> 8) & 32767u];
-      if (icm) r.cm[bh[k]] = pn + (uint32_t)(((int)(y[k] * 32767 - (int)(pn >> 8))) >> 2);
-      val = icm ? sp : (int)bh[k];
-      mine = hashed;
-    }
+    if (DM::HAS_HASHED) { val = (int)bh[k]; mine = hashed; }     // the bit history the ICM / ISSE map is indexed with
     if (DM::HAS_CM) {
       if (r.type == C_CM) {                                    // Predictor.cs:263-266, 365-373
         C.w.hmap4 = (int)(hmap_hi | idx[k]);
@@ -667,17 +663,22 @@ __device__ __forceinline__ void duo_coder_tick(const Shared& S, CoderCtx<DM::G>&
   const int lown = C.lring[slot + gl];
   int p = ((DM::LMASK >> gl) & 1u) ? lown : 0;    // a lead-role component's prediction is its ring entry
   if (DM::HAS_ISSE) {
-    // ---- ISSE, branch-free on all lanes (Predictor.cs:317-326, 440-449; the bit history was advanced by the lead role) ----
-    const bool isse = r.type == C_ISSE;
+    // ---- ICM + ISSE, branch-free on all lanes (Predictor.cs:267-272, 317-326, 375-381, 440-449): both index a map with
+    //      the bit history the history role found and advanced.  ISSE map: {weight, bias} pairs; ICM map: 22-bit
+    //      probabilities with a 4-byte stride.
+    const bool isse = r.type == C_ISSE, icm = r.type == C_ICM;
     const uint32_t bh = (uint32_t)lown & 255u;
-    const int2 wt = *reinterpret_cast<const int2*>(r.cm + bh * 2);
-    const int pe = clamp2k((wt.x * pj + wt.y * 64) >> 16);
+    const uint32_t i0 = icm ? bh : bh * 2u;
+    const int w0 = (int)r.cm[i0], w1 = (int)r.cm[isse ? i0 + 1u : i0];
+    const int sp = S.stretch[((uint32_t)w0 >> 8) & 32767u];
+    const int pe = clamp2k((w0 * pj + w1 * 64) >> 16);
     const int err = y * 32767 - (int)S.squash[pe + 2048];
-    int2 nw;
-    nw.x = clamp512k(wt.x + ((err * pj + (1 << 12)) >> 13));
-    nw.y = clamp512k(wt.y + ((err + 16) >> 5));
-    if (act && isse) *reinterpret_cast<int2*>(r.cm + bh * 2) = nw;
-    p = isse ? pe : p;
+    const int nw0 = isse ? clamp512k(w0 + ((err * pj + (1 << 12)) >> 13))
+                         : (int)((uint32_t)w0 + (uint32_t)(((int)(y * 32767 - (int)((uint32_t)w0 >> 8))) >> 2));
+    const int nw1 = clamp512k(w1 + ((err + 16) >> 5));
+    if (act && (isse || icm)) r.cm[i0] = (uint32_t)nw0;
+    if (act && isse) r.cm[i0 + 1u] = (uint32_t)nw1;
+    p = isse ? pe : (icm ? sp : p);
   }
   DM::lanes(S, C, r, pj, pk, y, act, t, p, gl);
   int pmv = 0;
@@ -750,13 +751,13 @@ __device__ __forceinline__ void duo_coder_body(const CodecParams& P, uint8_t* sm
   lane_load(S, P, w, r, gl < S.n ? gl : 0);
   if (gl >= S.n) { r.type = C_NONE; r.d = 0; r.srcj = r.srck = 0; }
   // maps live in the shared slice (the host launches this kernel only then): keep the pointer provably shared
-  r.cm = r.type == C_ISSE ? reinterpret_cast<uint32_t*>(w.slice + S.comp[gl < S.n ? gl : 0].smem_cm)
-                          : reinterpret_cast<uint32_t*>(const_cast<int16_t*>(S.stretch));
+  r.cm = (r.type == C_ISSE || r.type == C_ICM) ? reinterpret_cast<uint32_t*>(w.slice + S.comp[gl < S.n ? gl : 0].smem_cm)
+                                               : reinterpret_cast<uint32_t*>(const_cast<int16_t*>(S.stretch));
   CoderLane L;
   {
     const int tj = S.comp[r.srcj].type, tk = S.comp[r.srck].type;
-    L.jL = (tj == C_CONS || tj == C_CM || tj == C_ICM || tj == C_MATCH) ? 1 : 0;
-    L.kL = (tk == C_CONS || tk == C_CM || tk == C_ICM || tk == C_MATCH) ? 1 : 0;
+    L.jL = (tj == C_CONS || tj == C_CM || tj == C_MATCH) ? 1 : 0;
+    L.kL = (tk == C_CONS || tk == C_CM || tk == C_MATCH) ? 1 : 0;
     L.dj = (r.d - (int)S.comp[r.srcj].delay - 1) & 7;
     L.dk = (r.d - (int)S.comp[r.srck].delay - 1) & 7;
   }
@@ -951,7 +952,11 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
       sync->cpos = c;
       ++low;                         // encode(0, 0) in front of every byte, Encoder.cs:49
       normalise();
+#ifdef ZPQ_DUO_ARITH_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1     // rolled: this warp is never the slowest role, and 4 KB less hot code helps the other four
+#endif
       for (int k = 0; k < 8; ++k) {
         const int pf = pfring[(c * 8u + k) & (kDuoRing - 1)];
         const uint32_t pr = (uint32_t)S.squash[pf + 2048] * 2 + 1;
@@ -977,6 +982,19 @@ __device__ __forceinline__ void duo_arith_body(const CodecParams& P, uint8_t* sm
   ZPQ_T_REPORT("arith")
 }
 
+#ifndef ZPQ_DUO_ORDER
+#define ZPQ_DUO_ORDER 4123     // decimal digits, first body first: 0,4,1,2,3 (a leading zero would make it octal)
+#endif
+// role 0 context, 1 history, 2 coder, 3 mixer (only in a SPLIT model), 4 arithmetic coder
+template <class DM, int ROLE>
+__device__ __forceinline__ void duo_role_body(const CodecParams& P, uint8_t* smem, const Shared& S, int pair) {
+  if (ROLE == 0) duo_lead_body<DM, 0>(P, smem, S, pair);
+  else if (ROLE == 1) duo_lead_body<DM, 1>(P, smem, S, pair);
+  else if (ROLE == 2) duo_coder_body<DM, 1>(P, smem, S, pair);
+  else if (ROLE == 3) { if (DM::SPLIT) duo_coder_body<DM, 2>(P, smem, S, pair); }
+  else duo_arith_body<DM>(P, smem, S);
+}
+
 // Kernel body.  Per block group p: context role, history role, coder (prediction) role and, when the model's MIX
 // components can run on their own, mixer role -- warp 4p+r, so role r of every group lands on SM sub-partition r and
 // shares its instruction cache with copies of itself; the LAST warp is the arithmetic coder of every block of the CTA
@@ -987,12 +1005,16 @@ __device__ __forceinline__ void encode_duo_body(const CodecParams& P, uint8_t* s
   stage_shared(P, smem, S);
   constexpr int W = DM::SPLIT ? 4 : 3;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  if (warp == nwarps - 1) { duo_arith_body<DM>(P, smem, S); return; }
-  const int pair = warp / W, role = warp % W;
-  if (role == 0) duo_lead_body<DM, 0>(P, smem, S, pair);
-  else if (role == 1) duo_lead_body<DM, 1>(P, smem, S, pair);
-  else if (role == 2) duo_coder_body<DM, 1>(P, smem, S, pair);
-  else duo_coder_body<DM, 2>(P, smem, S, pair);
+  const int pair = warp / W, role = warp == nwarps - 1 ? 4 : warp % W;
+  // The order of the role bodies in the kernel image is a tuning knob: the hot loops of the five roles together are about
+  // as large as the SM's 32 KB instruction cache, and which of them collide depends on their addresses.
+  constexpr int O0 = ZPQ_DUO_ORDER / 10000 % 10, O1 = ZPQ_DUO_ORDER / 1000 % 10, O2 = ZPQ_DUO_ORDER / 100 % 10,
+                O3 = ZPQ_DUO_ORDER / 10 % 10, O4 = ZPQ_DUO_ORDER % 10;
+  if (role == O0) duo_role_body<DM, O0>(P, smem, S, pair);
+  else if (role == O1) duo_role_body<DM, O1>(P, smem, S, pair);
+  else if (role == O2) duo_role_body<DM, O2>(P, smem, S, pair);
+  else if (role == O3) duo_role_body<DM, O3>(P, smem, S, pair);
+  else duo_role_body<DM, O4>(P, smem, S, pair);
 }
 
 }  // namespace zpq

@@ -194,7 +194,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
     // two-role encoder: predictions of lead-role components (CONS/CM/ICM/MATCH) are read from the ring at any
     // distance; a prediction made by the coder role is read from its lane's history of the last 8 bits
     {
-      auto lead_type = [&](int t) { return t == C_CONS || t == C_CM || t == C_ICM || t == C_MATCH; };
+      auto lead_type = [&](int t) { return t == C_CONS || t == C_CM || t == C_MATCH; };   // (an ICM's map is trained by the coder role)
       std::vector<int> types(h.n);
       const uint8_t* q2 = &h.wire[7];
       for (int i = 0; i < h.n; ++i) { types[i] = q2[0]; q2 += comp_len(q2[0]); }
@@ -277,9 +277,9 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (bits > 26) throw Failure(ZPQ_E_CONFIG, "max size for ICM is 26");
         d.mask = (uint32_t)((64ull << bits) - 16);
         d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false, 3);
-        if (duo_g) {   // the history role owns ICM maps and addresses them with a 4-byte stride
-          if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 4, 0, true, 3); }
-          else { d.tab2 = take(1024); fill(d.tab2, 1024, 4, 0, false, 3); }
+        if (duo_g) {   // the coder role owns ICM maps and addresses them with a 4-byte stride
+          if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 4, 0, true, 1); }
+          else { d.tab2 = take(1024); fill(d.tab2, 1024, 4, 0, false, 1); }
         } else if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 1, 0, true); }
         else { d.tab2 = take(2048); fill(d.tab2, 2048, 1, 0, false); }
         break;
