@@ -17,6 +17,10 @@
     one-line helpers whose C# text is wrong (train, squash, stretch, clamp2k, clamp512k) are supplied by the
     harness as the reference's own JIT comments state them (Predictor.cs:916-921, 1031-1036, 1116-1121); the static
     tables come from the literals in the reference (tests/golden/reference_kat.json) -> libpredictor_ref.so (build_predictor())
+  * the block framing on top of that: Compressor.writeTag / startBlock / startSegment / postProcess / compress / endSegment /
+    endBlock, ZPAQL.read / write, Encoder.init / compress -> libcompressor_ref.so (build_compressor()); and the way back:
+    Decompresser.findBlock / findFilename / readComment / decompress / readSegmentEnd, Decoder.decompress / skip / init,
+    PostProcessor.init / write -> libdecompresser_ref.so (build_decompresser())
 
 Test infrastructure only.  Nothing is copied into the repository: the C text is read where it lies, three
 mechanical repairs of formatter damage are applied in memory (blank lines inside macro continuations, `budget.`
@@ -500,13 +504,237 @@ def build_predictor(force: bool = False) -> str | None:
     return PRED_OUT
 
 
+COMP_SRC = "/root/reference/ZPAQSharp/Compressor.cs"
+COMP_OUT = os.path.join(OUT_DIR, "libcompressor_ref.so")
+
+
+def compressor_text() -> str:
+    """The block FRAMING of the reference: Compressor.writeTag / startBlock(level) / startBlock(hcomp) / startSegment /
+    postProcess / compress / endSegment / endBlock (Compressor.cs:27-99, 133-249, 294-299), ZPAQL.read / write
+    (ZPAQL.cs:112-179) and Encoder.init / compress / encode (Encoder.cs:26-103) as they lie, on top of the predictor
+    fragment.  Textual repairs: C# `char[] x` -> `const char* x`, `= null` -> `= 0`, `Reader` / `Writer` parameters ->
+    the harness's handle types, one comment whose second slash the formatter ate, and postProcess's C#-ified signature
+    (`string pcomp, string comment`; its body still uses the C++ one: `const char* pcomp, int len`)."""
+    base = predictor_text()
+    fix = lambda t: re.sub(r"Array\.Resize\(ref\s+([\w\.]+),\s*", r"\1.resize(", t).replace(".Length", ".size()").replace("@", "")
+    cs = lambda t: re.sub(r"\bchar\[\]\s+(\w+)", r"const char* \1", fix(t)).replace("= null", "= 0")
+    rd = cs(_method_text(ZPAQL_SRC, "int read(Reader in2) // Read header")).replace("int read(Reader in2)", "int read(ReaderRef in2)")
+    rd = re.sub(r"(?m)^(\s*)/ Get header", r"\1// Get header", rd)
+    wr = cs(_method_text(ZPAQL_SRC, "bool write(Writer out2, bool pp)")).replace("bool write(Writer out2, bool pp)", "bool write(WriterRef out2, bool pp)")
+    e_init = cs(_method_text(ENC_SRC, "void init()"))
+    e_comp = cs(_method_text(ENC_SRC, "void compress(int c) // c is 0..255 or EOF"))
+    e_enc = _method_text(ENC_SRC, "void encode(int y, int p)")
+    c_tag = cs(_method_text(COMP_SRC, "void writeTag()"))
+    c_lvl = cs(_method_text(COMP_SRC, "void startBlock(int level)"))
+    c_hc = cs(_method_text(COMP_SRC, "void startBlock(char[] hcomp)"))
+    c_seg = cs(_method_text(COMP_SRC, "void startSegment(char[] filename = null, char[] comment = null)"))
+    c_pp = cs(_method_text(COMP_SRC, "void postProcess(string pcomp = null, string comment = null)"))
+    assert "postProcess(string pcomp = 0, string comment = 0)" in c_pp
+    c_pp = c_pp.replace("postProcess(string pcomp = 0, string comment = 0)", "postProcess(const char* pcomp = 0, int len = 0)")
+    c_cmp = cs(_method_text(COMP_SRC, "bool compress(int n = -1)"))
+    c_end = cs(_method_text(COMP_SRC, "void endSegment(char[] sha1string = null)"))
+    c_eb = cs(_method_text(COMP_SRC, "void endBlock()"))
+    # ZPAQL.read uses compsize: it has to be declared in front of the interpreter struct
+    csz = "static const int compsize[256] = {0, 2, 3, 2, 3, 4, 6, 6, 3, 5};          // Component.cs:27-43\n"
+    assert base.count(csz) == 1 and base.count("struct RefVM {") == 1
+    base = base.replace(csz, "").replace("struct RefVM {", csz + r"""
+struct RefSink { unsigned char* p; unsigned long long cap, n; void put(int c) { if (n < cap) p[n] = (unsigned char)c; ++n; } };
+struct Reader { virtual int get() = 0;                                       // libzpaq Reader (LICENSE / libzpaq.h): get(), read()
+                virtual int read(char* buf, int n) { int i = 0, c; while (i < n && (c = get()) >= 0) buf[i++] = (char)c; return i; } };
+struct ReaderRef { Reader* r; ReaderRef(Reader* r_ = 0) : r(r_) {} int get() { return r->get(); } int read(char* b, int n) { return r->read(b, n); } };
+struct WriterRef { RefSink* s; WriterRef(RefSink* s_ = 0) : s(s_) {} void put(int c) { s->put(c & 255); }
+                   void write(const char* b, int n) { for (int i = 0; i < n; ++i) put(b[i]); } };
+struct RefVM {""", 1)
+    tail_vm = "  uint H(int i) { return hv(i); }\n};"
+    assert base.count(tail_vm) == 1
+    base = base.replace(tail_vm, "  uint H(int i) { return hv(i); }\n  void* rcode; int rcode_size;\n" + rd + "\n" + wr + "\n};", 1)
+    dup = "struct RefSink { unsigned char* p; unsigned long long cap, n; void put(int c) { if (n < cap) p[n] = (unsigned char)c; ++n; } };\nstruct RefBlockEncoder {"
+    assert base.count(dup) == 1
+    base = base.replace(dup, "struct RefBlockEncoder {", 1)
+    return base + r"""
+static int toushort(const char* p) { return (p[0] & 255) + 256 * (p[1] & 255); }      // libzpaq toU16
+struct RefPredictorN : RefPredictor { int predict() { return predict0(); } void update(int y) { update0(y); } };   // Predictor.cs:176-180, 200-204 (NOJIT)
+struct RefEncoder {                                    // Encoder.cs:15-103: init, compress, encode are reference text
+  WriterRef out; uint low, high; RefPredictorN pr; Arr<char> buf;
+""" + e_init + "\n" + e_comp + "\n" + e_enc + r"""
+};
+struct MemoryReader : Reader {                         // Compressor.cs:324-340
+  const char* p; MemoryReader(const char* p_, int off) : p(p_ + off) {} MemoryReader(MemoryReader* o) : p(o->p) {}
+  int get() { return *p++ & 255; }
+};
+struct BoundedReader : Reader { const unsigned char* p; unsigned long long n, i; int get() { return i < n ? p[i++] : -1; } };
+struct RefSHA1 { void put(int) {} unsigned long long usize() { return 0; } const char* result() { return 0; } };
+struct RefPZ { Arr<byte> header; int hbegin, hend; RefSHA1* sha1; void initp() {} void run(int) {} void flush() {} };
+enum State { INIT, BLOCK1, SEG1, BLOCK2, SEG2 };       // Compressor.cs:314-322
+struct RefCompressor {
+  RefEncoder enc; RefVM& z; RefPZ pz; ReaderRef in; RefSHA1 sha1; State state; bool verify;
+  RefCompressor() : z(enc.pr.z), state(INIT), verify(false) { pz.hbegin = pz.hend = 0; pz.sha1 = 0; }
+""" + "\n".join([c_tag, c_lvl, c_hc, c_seg, c_pp, c_cmp, c_end, c_eb]) + r"""
+};
+// One archive block exactly as LibZPAQ.compressBlock drives the Compressor (LibZPAQ.cs:296-325): [writeTag,] startBlock,
+// startSegment(filename, comment), postProcess(pcomp, len), compress() to EOF, endSegment(sha1), endBlock.
+// level > 0: startBlock(int level) and the reference's own model table; else startBlock(hcomp) with `hdr`.
+extern "C" long long ref_compress_block(int level, const unsigned char* hdr, const unsigned char* pcomp, int pcomp_len,
+                                        const char* filename, const char* comment, const unsigned char* input, unsigned long long n,
+                                        const unsigned char* sha1string, int with_tag, unsigned char* out, unsigned long long cap) {
+  try {
+    RefCompressor* co = new RefCompressor();
+    RefPredictor& P = co->enc.pr;
+    P.initTables = false; P.pcode = 0; P.pcode_size = 0; P.c8 = 1; P.hmap4 = 1;
+    RefSink sink; sink.p = out; sink.cap = cap; sink.n = 0;
+    co->enc.out = WriterRef(&sink); co->enc.low = 1; co->enc.high = 0xFFFFFFFFu;
+    if (with_tag) co->writeTag();
+    if (level > 0) co->startBlock(level); else co->startBlock((const char*)hdr);
+    co->startSegment(filename, comment);
+    co->postProcess(pcomp_len > 0 ? (const char*)pcomp : 0, pcomp_len);
+    BoundedReader br; br.p = input; br.n = n; br.i = 0;
+    co->in = ReaderRef(&br);
+    while (co->compress(1 << 20)) ;
+    co->endSegment((const char*)sha1string);
+    co->endBlock();
+    delete co;
+    return (long long)sink.n;
+  } catch (const std::exception&) { return -1; }
+}
+"""
+
+
+def build_compressor(force: bool = False) -> str | None:
+    if not (os.path.exists(COMP_SRC) and os.path.exists(PRED_SRC) and os.path.exists(ZPAQL_SRC)):
+        return COMP_OUT if os.path.exists(COMP_OUT) else None
+    if os.path.exists(COMP_OUT) and not force and os.path.getmtime(COMP_OUT) >= os.path.getmtime(__file__):
+        return COMP_OUT
+    os.makedirs(OUT_DIR, exist_ok=True)
+    p = subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-w", "-fpermissive", "-std=c++14", "-x", "c++", "-", "-o", COMP_OUT],
+                       input=compressor_text().encode(), capture_output=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stderr.decode()[:8000])
+        return None
+    return COMP_OUT
+
+
+DECOMP_SRC = "/root/reference/ZPAQSharp/Decompresser.cs"
+PP_SRC = "/root/reference/ZPAQSharp/PostProcessor.cs"
+DECOMP_OUT = os.path.join(OUT_DIR, "libdecompresser_ref.so")
+
+
+def decompresser_text() -> str:
+    """The DECODE side of the framing: Decompresser.findBlock / findFilename / readComment / decompress / readSegmentEnd
+    (Decompresser.cs:29-194), Decoder.decompress / skip / init / decode (Decoder.cs:32-111, 136-158), PostProcessor.init /
+    write / getState (PostProcessor.cs:27-91) and ZPAQL.flush (ZPAQL.cs:194-199) as they lie, on top of the compressor
+    fragment, driven like LibZPAQ.decompress (LibZPAQ.cs:65-79).  Textual repairs as before plus: `nt c` -> `int c`
+    (Decoder.cs:70), and the C#-ified signatures of findFilename / readComment / readSegmentEnd whose bodies still use the
+    C++ parameter names (filename, comment, sha1string as a writable buffer).  Supplied by the harness because their C#
+    text is not C++ any more: Decoder.get (unbuffered here), ZPAQL.outc (Decoder.cs:113-123, ZPAQL.cs:201-207: the
+    comma of libzpaq's `(outbuf[bufptr]=ch, ++bufptr==size)` became `&&`), ZPAQL.clear / initp (H and M are `hv` / `mv` here)."""
+    base = compressor_text()
+    fix = lambda t: re.sub(r"Array\.Resize\(ref\s+([\w\.]+),\s*", r"\1.resize(", t).replace(".Length", ".size()").replace("@", "")
+    cs = lambda t: fix(t).replace("= null", "= 0")
+    flush = cs(_method_text(ZPAQL_SRC, "void flush() // write outbuf"))
+    d_dec = cs(_method_text(DEC_SRC, "int decompress() // return a byte or EOF"))
+    d_skip = cs(_method_text(DEC_SRC, "int skip() // skip to the end of the segment"))
+    assert "\tnt c = -1;" in d_skip.replace("    ", "\t") or "nt c = -1;" in d_skip
+    d_skip = re.sub(r"(?m)^(\s*)nt c = -1;", r"\1int c = -1;", d_skip)
+    d_init = cs(_method_text(DEC_SRC, "void init() // initialize at start of block"))
+    d_bit = _method_text(DEC_SRC, "int decode(int p)")
+    p_init = cs(_method_text(PP_SRC, "void init(int h, int m)"))
+    p_write = cs(_method_text(PP_SRC, "int write(int c) // Input a byte, return state"))
+    p_state = cs(_method_text(PP_SRC, "int getState()"))
+    f_blk = cs(_method_text(DECOMP_SRC, "bool findBlock(double* memptr = null)"))
+    f_name = cs(_method_text(DECOMP_SRC, "bool findFilename(Writer out2 = null)")).replace("findFilename(Writer out2 = 0)", "findFilename(WriterRef filename = 0)")
+    f_cmt = cs(_method_text(DECOMP_SRC, "void readComment(Writer out2 = null)")).replace("readComment(Writer out2 = 0)", "readComment(WriterRef comment = 0)")
+    f_dec = cs(_method_text(DECOMP_SRC, "bool decompress(int n = -1)"))
+    f_end = cs(_method_text(DECOMP_SRC, "void readSegmentEnd(char[] sha1string = null)")).replace("readSegmentEnd(char[] sha1string = 0)", "readSegmentEnd(char* sha1string = 0)")
+    assert "WriterRef filename" in f_name and "WriterRef comment" in f_cmt and "char* sha1string" in f_end
+    stub = "  void outc(int) {}\n"
+    assert base.count(stub) == 1
+    base = base.replace(stub, r"""  WriterRef output; ShaRef sha1; Arr<char> outbuf; int bufptr;
+  void outc(int ch) { if (ch < 0 || (outbuf[bufptr] = ch, ++bufptr == (int)outbuf.size())) flush(); }   // libzpaq ZPAQL::outc
+""" + flush + r"""
+  void clear() { cend = hbegin = hend = 0; a = b = c = d = 0; f = pc = 0; header.resize(0); hv.resize(0); mv.resize(0); memset(r, 0, sizeof r); }  // ZPAQL.cs:33-42
+  void initp() { hv.resize(1, header[4]); mv.resize(1, header[5]); memset(r, 0, sizeof r); a = b = c = d = 0; f = 0; pc = 0; }   // ZPAQL.cs:52-56, 1010-1026
+  double memory() { return 0; }
+""", 1)
+    wref = "struct WriterRef { RefSink* s; WriterRef(RefSink* s_ = 0) : s(s_) {} void put(int c) { s->put(c & 255); }"
+    assert base.count(wref) == 1
+    base = base.replace(wref, wref + " explicit operator bool() const { return s != 0; }", 1)
+    base = base.replace("struct RefVM {", "struct ShaRef { explicit operator bool() const { return false; } void write(const char*, int) {} };\nstruct RefVM {", 1)
+    return base + r"""
+struct RefDecoder : Reader {                           // Decoder.cs:16-159: decompress, skip, init, decode are reference text
+  ReaderRef in; uint low, high, curr; RefPredictorN pr;
+  int get() { return in.get(); }                       // Decoder.cs:113-123 reads `in` through a 64 KB buffer
+""" + "\n".join([d_dec, d_skip, d_init, d_bit]) + r"""
+};
+struct RefPostProcessor {                              // PostProcessor.cs:11-101
+  int state, hsize, ph, pm; RefVM z;
+""" + "\n".join([p_init, p_write, p_state]) + r"""
+};
+enum DState { BLOCK, FILENAME, COMMENT, DATA, SEGEND };   // Decompresser.cs:206-219
+enum DecodeState { FIRSTSEG, SEG, SKIP };
+struct RefDecompresser {
+  RefDecoder dec; RefVM& z; RefPostProcessor pp; DState state; DecodeState decode_state;
+  RefDecompresser() : z(dec.pr.z), state(BLOCK), decode_state(FIRSTSEG) {
+    RefPredictor& P = dec.pr; P.initTables = false; P.pcode = 0; P.pcode_size = 0; P.c8 = 1; P.hmap4 = 1;
+    dec.low = 1; dec.high = 0xFFFFFFFFu; dec.curr = 0;
+    z.outbuf.resize(1 << 14); z.bufptr = 0; pp.z.outbuf.resize(1 << 14); pp.z.bufptr = 0;
+    pp.state = pp.hsize = pp.ph = pp.pm = 0; pp.z.cend = pp.z.hbegin = pp.z.hend = 0; pp.z.rcode = 0; pp.z.rcode_size = 0; z.rcode = 0; z.rcode_size = 0;
+  }
+""" + "\n".join([f_blk, f_name, f_cmt, f_dec, f_end]) + r"""
+};
+// LibZPAQ.decompress (LibZPAQ.cs:65-79): every segment of every block of `arc` into `out`; per segment 21 bytes into
+// `marks` (readSegmentEnd: 0 = no checksum, else 1 + the stored SHA-1).  Returns bytes written, -1 on a reference error.
+extern "C" long long ref_decompress(const unsigned char* arc, unsigned long long n, unsigned char* out, unsigned long long cap,
+                                    unsigned char* marks, int max_segs, int* nsegs) {
+  *nsegs = 0;
+  try {
+    RefDecompresser* d = new RefDecompresser();
+    BoundedReader br; br.p = arc; br.n = n; br.i = 0;
+    d->dec.in = ReaderRef(&br);
+    RefSink sink; sink.p = out; sink.cap = cap; sink.n = 0;
+    d->pp.z.output = WriterRef(&sink);
+    while (d->findBlock()) {
+      while (d->findFilename()) {
+        d->readComment();
+        d->decompress();
+        char s[21]; memset(s, 0, sizeof s);
+        d->readSegmentEnd(s);
+        if (*nsegs < max_segs) memcpy(marks + 21 * *nsegs, s, 21);
+        ++*nsegs;
+      }
+    }
+    delete d;
+    return (long long)sink.n;
+  } catch (const std::exception&) { return -1; }
+}
+"""
+
+
+def build_decompresser(force: bool = False) -> str | None:
+    if not all(os.path.exists(f) for f in (DECOMP_SRC, PP_SRC, DEC_SRC, COMP_SRC, PRED_SRC, ZPAQL_SRC)):
+        return DECOMP_OUT if os.path.exists(DECOMP_OUT) else None
+    if os.path.exists(DECOMP_OUT) and not force and os.path.getmtime(DECOMP_OUT) >= os.path.getmtime(__file__):
+        return DECOMP_OUT
+    os.makedirs(OUT_DIR, exist_ok=True)
+    p = subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-w", "-fpermissive", "-std=c++14", "-x", "c++", "-", "-o", DECOMP_OUT],
+                       input=decompresser_text().encode(), capture_output=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stderr.decode()[:8000])
+        return None
+    return DECOMP_OUT
+
+
 def build_all(force: bool = False) -> dict:
     """Every fragment; returns {name: path or None}."""
     return {"divsufsort": build(force), "lzbuffer": build_lzbuffer(force), "coder": build_coder(force), "zpaql": build_zpaql(force),
-            "predictor": build_predictor(force)}
+            "predictor": build_predictor(force), "compressor": build_compressor(force),
+            "decompresser": build_decompresser(force)}
 
 
 if __name__ == "__main__":
+    r6 = build_compressor(force=True)
+    print(r6 or "reference Compressor framing did not build")
+    r7 = build_decompresser(force=True)
+    print(r7 or "reference Decompresser did not build")
     r5 = build_predictor(force=True)
     print(r5 or "reference predictor did not build")
     r4 = build_zpaql(force=True)
@@ -517,4 +745,4 @@ if __name__ == "__main__":
     print(r or "reference suffix sorter did not build")
     r2 = build_lzbuffer(force=True)
     print(r2 or "reference LZBuffer did not build")
-    sys.exit(0 if r and r2 and r3 and r4 and r5 else 1)
+    sys.exit(0 if r and r2 and r3 and r4 and r5 and r6 and r7 else 1)

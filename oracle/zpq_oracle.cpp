@@ -7,7 +7,8 @@
 // it; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs use it.
 //
-// PARITY STATUS: pinned against the reference's own code for the arithmetic of the path, unpinned only for framing.
+// PARITY STATUS: pinned against the reference's own code for the block codec (arithmetic and framing, both directions);
+// restated only: the config-text front end (makeConfig, ZPAQL assembler) and SHA-1.
 // The reference ships no archive and no expected-output vector and cannot be built as a whole (no .NET toolchain, not
 // valid C#), but the C / C++ text it still carries compiles: oracle/build_ref.py reads it where it
 // lies under /root/reference, applies textual repairs in memory and builds oracle/_ref/*.so, and the tests compare this
@@ -21,11 +22,15 @@
 //   tests/test_reference_lzbuffer.py    LZBuffer (LZBuffer.cs:151-486) and e8e9 (LibZPAQ.cs:371-384): LZ77 both formats, both
 //                                       matchers, BWT, with and without E8E9
 //   tests/test_reference_divsufsort.py  divsufsort (divsufsort.cs:1940): suffix arrays, BWT streams
+//   tests/test_reference_compressor.py  Compressor framing + ZPAQL.read/write + Encoder.init/compress (Compressor.cs:27-299):
+//                                       whole archive blocks, levels 1-3 and 10 method strings, stored mode
+//   tests/test_reference_decompresser.py Decompresser + Decoder.decompress/skip + PostProcessor (Decompresser.cs:29-194):
+//                                       the reference text restores the input from this file's archives
 // Pinned against the reference's literals (tests/golden/reference_kat.json, extracted by tests/golden/make_golden.py): the
 // state table, squash/stretch/dt/dt2k tables and their checksums, the three built-in model bytecodes (Compiler known
 // answer), compsize[], the locator tag and rolling-hash constants, and the hand-checkable stored-mode framing.
-// Restated only (no compilable reference text): block / segment framing beyond those known answers, makeConfig and the
-// ZPAQL assembler beyond the three bytecodes, the PostProcessor state machine, SHA-1 (FIPS 180, checked against hashlib).
+// Restated only (no compilable reference text): makeConfig and the ZPAQL assembler beyond the three bytecodes, SHA-1
+// (FIPS 180, checked against hashlib).
 //
 // Each function cites the reference file:line (relative to /root/reference/ZPAQSharp) whose
 // behaviour it follows.  Where the C# text is known to be corrupt
