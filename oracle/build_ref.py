@@ -21,6 +21,8 @@
     endBlock, ZPAQL.read / write, Encoder.init / compress -> libcompressor_ref.so (build_compressor()); and the way back:
     Decompresser.findBlock / findFilename / readComment / decompress / readSegmentEnd, Decoder.decompress / skip / init,
     PostProcessor.init / write -> libdecompresser_ref.so (build_decompresser())
+  * makeConfig, itos and the numeric-method expansion inside compressBlock (LibZPAQ.cs:125-290, 360-367, 388-1044), still
+    C++ text -> libfrontend_ref.so (build_frontend())
 
 Test infrastructure only.  Nothing is copied into the repository: the C text is read where it lies, three
 mechanical repairs of formatter damage are applied in memory (blank lines inside macro continuations, `budget.`
@@ -723,11 +725,77 @@ def build_decompresser(force: bool = False) -> str | None:
     return DECOMP_OUT
 
 
+LIBZ_SRC = "/root/reference/ZPAQSharp/LibZPAQ.cs"
+FRONT_OUT = os.path.join(OUT_DIR, "libfrontend_ref.so")
+
+
+def frontend_text() -> str:
+    """The method-string front end of the reference, still pristine C++ inside LibZPAQ.cs: makeConfig (LibZPAQ.cs:388-1044,
+    method string -> config text + args[9]), itos (:360-367), and the statement range of compressBlock that derives the
+    block-size argument and expands a numeric method "LB,R,t" into its x-method (:125-141, 158-290; the SHA-1 statements
+    in between are left out).  lg / nbits come from LZBuffer.cs:118-135.  Repairs: `char[] method` -> `const char*`,
+    `.Length` -> `.size()`, C# `in` / `@in` -> the harness's buffer, `MAX`."""
+    mk = _method_text(LIBZ_SRC, "string makeConfig(char[] method, int args[])").replace(
+        "string makeConfig(char[] method, int args[])", "string makeConfig(const char* method, int args[])").replace(".Length", ".size()")
+    itos = _method_text(LIBZ_SRC, "string itos(long x, int n = 1)")
+    lg = _method_text(LZ_SRC, "int lg(unsigned x)")
+    nb = _method_text(LZ_SRC, "int nbits(unsigned x)")
+    lines = open(LIBZ_SRC, encoding="utf-8-sig").read().split("\n")
+    i0 = next(i for i, l in enumerate(lines) if "const unsigned n =in.Length;" in l)
+    i1 = next(i for i, l in enumerate(lines) if "// Get hash of input" in l)
+    i2 = next(i for i, l in enumerate(lines) if "// Expand default methods" in l)
+    i3 = next(i for i, l in enumerate(lines) if l.strip() == "// Compress" and i > i2)
+    assert i0 < i1 < i2 < i3
+    expand = "\n".join(lines[i0:i1] + lines[i2:i3])
+    expand = expand.replace("=in.Length", "= in.size()").replace("in.data()", "in.data()").replace(".Length", ".size()").replace("@", "")
+    return r"""
+#include <string>
+#include <vector>
+#include <ctype.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdexcept>
+using std::string;
+#define assert(x) ((void)0)
+#define MAX(a, b) ((a) > (b) ? (a) : (b))
+static void error(const char* msg) { throw std::runtime_error(msg); }
+""" + "\n".join([lg, nb, itos, mk]) + r"""
+struct InBuf { const unsigned char* p; unsigned n; unsigned size() const { return n; } const unsigned char* data() const { return p; } };
+static string expandMethod(InBuf in, string method) {
+""" + expand + r"""
+  return method;
+}
+extern "C" int ref_make_config(const char* method, int* args, char* out, int cap) {
+  try { string s = makeConfig(method, args); if ((int)s.size() >= cap) return -2; memcpy(out, s.c_str(), s.size() + 1); return (int)s.size(); }
+  catch (const std::exception&) { return -1; }
+}
+extern "C" int ref_expand_method(const char* method, const unsigned char* data, unsigned n, char* out, int cap) {
+  try { InBuf in; in.p = data; in.n = n; string s = expandMethod(in, method); if ((int)s.size() >= cap) return -2;
+        memcpy(out, s.c_str(), s.size() + 1); return (int)s.size(); }
+  catch (const std::exception&) { return -1; }
+}
+"""
+
+
+def build_frontend(force: bool = False) -> str | None:
+    if not (os.path.exists(LIBZ_SRC) and os.path.exists(LZ_SRC)):
+        return FRONT_OUT if os.path.exists(FRONT_OUT) else None
+    if os.path.exists(FRONT_OUT) and not force and os.path.getmtime(FRONT_OUT) >= os.path.getmtime(__file__):
+        return FRONT_OUT
+    os.makedirs(OUT_DIR, exist_ok=True)
+    p = subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-fpermissive", "-std=c++14", "-x", "c++", "-", "-o", FRONT_OUT],
+                       input=frontend_text().encode(), capture_output=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stderr.decode()[:8000])
+        return None
+    return FRONT_OUT
+
+
 def build_all(force: bool = False) -> dict:
     """Every fragment; returns {name: path or None}."""
     return {"divsufsort": build(force), "lzbuffer": build_lzbuffer(force), "coder": build_coder(force), "zpaql": build_zpaql(force),
             "predictor": build_predictor(force), "compressor": build_compressor(force),
-            "decompresser": build_decompresser(force)}
+            "decompresser": build_decompresser(force), "frontend": build_frontend(force)}
 
 
 if __name__ == "__main__":
@@ -735,6 +803,8 @@ if __name__ == "__main__":
     print(r6 or "reference Compressor framing did not build")
     r7 = build_decompresser(force=True)
     print(r7 or "reference Decompresser did not build")
+    r8 = build_frontend(force=True)
+    print(r8 or "reference makeConfig / method expansion did not build")
     r5 = build_predictor(force=True)
     print(r5 or "reference predictor did not build")
     r4 = build_zpaql(force=True)
@@ -745,4 +815,4 @@ if __name__ == "__main__":
     print(r or "reference suffix sorter did not build")
     r2 = build_lzbuffer(force=True)
     print(r2 or "reference LZBuffer did not build")
-    sys.exit(0 if r and r2 and r3 and r4 and r5 and r6 and r7 else 1)
+    sys.exit(0 if r and r2 and r3 and r4 and r5 and r6 and r7 and r8 else 1)

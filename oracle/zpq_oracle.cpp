@@ -8,7 +8,7 @@
 // legs use it.
 //
 // PARITY STATUS: pinned against the reference's own code for the block codec (arithmetic and framing, both directions);
-// restated only: the config-text front end (makeConfig, ZPAQL assembler) and SHA-1.
+// and for the method-string front end; restated only: the ZPAQL assembler (Compiler.cs) and SHA-1.
 // The reference ships no archive and no expected-output vector and cannot be built as a whole (no .NET toolchain, not
 // valid C#), but the C / C++ text it still carries compiles: oracle/build_ref.py reads it where it
 // lies under /root/reference, applies textual repairs in memory and builds oracle/_ref/*.so, and the tests compare this
@@ -29,8 +29,10 @@
 // Pinned against the reference's literals (tests/golden/reference_kat.json, extracted by tests/golden/make_golden.py): the
 // state table, squash/stretch/dt/dt2k tables and their checksums, the three built-in model bytecodes (Compiler known
 // answer), compsize[], the locator tag and rolling-hash constants, and the hand-checkable stored-mode framing.
-// Restated only (no compilable reference text): makeConfig and the ZPAQL assembler beyond the three bytecodes, SHA-1
-// (FIPS 180, checked against hashlib).
+//   tests/test_reference_frontend.py    makeConfig and the numeric-method expansion of compressBlock (LibZPAQ.cs:125-290,
+//                                       388-1044) against oracle/frontend.py: arguments and ZPAQL token streams
+// Restated only (no compilable reference text): the ZPAQL assembler beyond the three bytecodes, SHA-1 (FIPS 180, checked
+// against hashlib).
 //
 // Each function cites the reference file:line (relative to /root/reference/ZPAQSharp) whose
 // behaviour it follows.  Where the C# text is known to be corrupt
