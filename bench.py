@@ -138,9 +138,57 @@ def _reference_block_coder():
     return code
 
 
+def _reference_block_codec():
+    """The reference's own text for the WHOLE block path, when oracle/_ref holds it: Compressor.writeTag / startBlock(level) /
+    startSegment / postProcess / compress / endSegment / endBlock over Encoder, Predictor and ZPAQL text, and the way back
+    through Decompresser / Decoder / PostProcessor (oracle/build_ref.py; prebuilt, nothing is read from /root/reference at
+    run time).  Returns (compress(block) -> archive block, decompress(archive, n) -> bytes) or None."""
+    import ctypes as C
+    import hashlib
+    try:
+        from oracle import build_ref
+        pc, pd = build_ref.build_compressor(), build_ref.build_decompresser()
+        if not pc or not pd or not os.path.exists(pc) or not os.path.exists(pd):
+            return None
+        kat = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kat.json")))
+        tabs = [np.asarray(kat["sdt2k"], dtype=np.int32), np.asarray(kat["sdt"], dtype=np.int32), np.asarray(kat["ssquasht"], dtype=np.uint16),
+                np.asarray(kat["stdt"], dtype=np.int32), np.asarray(kat["sns"], dtype=np.uint8)]
+        Lc, Ld = C.CDLL(pc), C.CDLL(pd)
+        for L in (Lc, Ld):
+            L.ref_predictor_tables.argtypes = [C.c_void_p] * 5
+            L.ref_predictor_tables(*[t.ctypes.data for t in tabs])
+        Lc.ref_compress_block.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_ulonglong,
+                                          C.c_char_p, C.c_int, C.c_void_p, C.c_ulonglong]
+        Lc.ref_compress_block.restype = C.c_longlong
+        Ld.ref_decompress.argtypes = [C.c_char_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        Ld.ref_decompress.restype = C.c_longlong
+    except Exception:
+        return None
+
+    def comp(b):
+        sha = hashlib.sha1(b).digest()              # compressBlock hashes the block first (LibZPAQ.cs:143-155; the SHA1 class itself is missing)
+        cap = len(b) + len(b) // 4 + 4096
+        out = C.create_string_buffer(cap)
+        n = Lc.ref_compress_block(LEVEL, None, None, 0, None, str(len(b)).encode(), b, len(b), sha, 1, out, cap)   # ctypes releases the GIL
+        if n < 0 or n > cap:
+            raise RuntimeError("reference Compressor text failed")
+        return out.raw[:n]
+
+    def decomp(a, n):
+        out = C.create_string_buffer(n + 64)
+        marks = C.create_string_buffer(21 * 4)
+        nseg = C.c_int(0)
+        m = Ld.ref_decompress(a, len(a), out, n + 64, marks, 4, C.byref(nseg))
+        if m < 0:
+            raise RuntimeError("reference Decompresser text failed")
+        return out.raw[:m]
+    return comp, decomp
+
+
 def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
-    """Time the CPU path (one block per host thread) on a bounded sample of the workload: the reference's own text for the
-    per-bit hot loop when oracle/_ref holds it (kind "reference"), else the oracle port (kind "port")."""
+    """Time the CPU path (one block per host thread) on a bounded sample of the workload: the reference's own text when
+    oracle/_ref holds it (kind "reference": the whole Compressor / Decompresser path, else only the per-bit hot loop), else
+    the oracle port (kind "port")."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle as po
     from tools import synth
@@ -148,7 +196,8 @@ def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
     cores = os.cpu_count() or 1
     data = synth.blocks("mixed", 0, cores, BLOCK)
     blocks = [data[i * BLOCK:(i + 1) * BLOCK].tobytes() for i in range(cores)]
-    ref_code = _reference_block_coder()
+    codec = _reference_block_codec()
+    ref_code = None if codec else _reference_block_coder()
 
     def comp(b):
         return po.compress_block_level(b, LEVEL)
@@ -160,7 +209,18 @@ def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
     out = {"value": cores * BLOCK / 1e6 / t_port, "unit": "MB/s", "cores": cores, "kind": "port",
            "sample": "%d blocks of %d B (one per host thread), mid.cfg, oracle C++ -O2" % (cores, BLOCK),
            "seconds": t_port}
-    if ref_code is not None:
+    if codec is not None:
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            rarcs = list(ex.map(codec[0], blocks))
+        t_ref = time.perf_counter() - t0
+        assert rarcs == arcs, "reference text and oracle disagree"          # whole archive blocks, byte for byte
+        out.update({"value": cores * BLOCK / 1e6 / t_ref, "kind": "reference", "seconds": t_ref, "port_value": cores * BLOCK / 1e6 / t_port,
+                    "sample": "%d blocks of %d B (one per host thread), mid.cfg; the reference's own Compressor.startBlock(2) .. endBlock "
+                              "path (Compressor, Encoder, Predictor.init/predict0/update0/find, ZPAQL text compiled -O2 from "
+                              "/root/reference by oracle/build_ref.py, + SHA-1 of the block); archive blocks checked byte for byte "
+                              "against the oracle's" % (cores, BLOCK)})
+    elif ref_code is not None:
         t0 = time.perf_counter()
         with ThreadPoolExecutor(cores) as ex:
             coded = list(ex.map(ref_code, blocks))
@@ -173,14 +233,16 @@ def cpu_baseline(seconds_budget: float = 20.0, decompress: bool = True):
                               "ZPAQL.execute and Encoder.encode text compiled -O2 from /root/reference by oracle/build_ref.py "
                               "(+ SHA-1 of the block); coded bytes checked against the oracle's archives" % (cores, BLOCK)})
     if decompress and out["seconds"] < seconds_budget:
+        dec = (lambda a: codec[1](a, BLOCK)) if codec else (lambda a: po.decompress(a, cap=BLOCK + 64)[0])
         t0 = time.perf_counter()
         with ThreadPoolExecutor(cores) as ex:
-            back = list(ex.map(lambda a: po.decompress(a, cap=BLOCK + 64)[0], arcs))
+            back = list(ex.map(dec, arcs))
         t_d = time.perf_counter() - t0
         assert all(b == s for b, s in zip(back, blocks))
-        out["decompress_value"] = cores * BLOCK / 1e6 / t_d        # (oracle port: the reference's Decoder loop is not assembled)
+        out["decompress_value"] = cores * BLOCK / 1e6 / t_d        # the reference's Decompresser text when present, else the oracle port
+        out["decompress_kind"] = "reference" if codec else "port"
     t0 = time.perf_counter()
-    (ref_code or comp)(blocks[0])
+    (codec[0] if codec else (ref_code or comp))(blocks[0])
     out["single_core_value"] = BLOCK / 1e6 / (time.perf_counter() - t0)
     return out
 
@@ -210,7 +272,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": cfg, "cpu_baseline": base,
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "kind reference: Predictor/ZPAQL/Encoder text of the reference compiled from /root/reference (oracle/build_ref.py); "
+        "note": "kind reference: Compressor/Encoder/Predictor/ZPAQL text of the reference compiled from /root/reference (oracle/build_ref.py); "
                 "kind port: the C++ oracle restating it (ZPAQSharp as a whole is not buildable)",
     })
 
