@@ -1,0 +1,40 @@
+"""Host-side pieces of bench.py that run without a GPU: the CPU baseline's reference codec (the reference's Compressor /
+Decompresser text from oracle/_ref) must agree with the oracle and round-trip, and the reference arm must print the one
+JSON line the bench contract asks for."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_reference_codec_of_the_cpu_baseline_matches_oracle_and_round_trips():
+    import bench
+    from oracle import pyoracle as po
+    from tools import synth
+    codec = bench._reference_block_codec()
+    if codec is None:
+        pytest.skip("oracle/_ref fragments not available")
+    comp, decomp = codec
+    for n in (0, 1, 40000):
+        data = synth.blocks("mixed", 5, 1, max(n, 1)).tobytes()[:n]
+        arc = comp(data)
+        assert arc == po.compress_block_level(data, bench.LEVEL)
+        assert decomp(arc, len(data)) == data
+
+
+def test_reference_arm_prints_one_json_line():
+    env = dict(os.environ)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "MB/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
