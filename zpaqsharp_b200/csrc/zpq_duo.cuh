@@ -1005,7 +1005,11 @@ __device__ __forceinline__ void encode_duo_body(const CodecParams& P, uint8_t* s
   stage_shared(P, smem, S);
   constexpr int W = DM::SPLIT ? 4 : 3;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#ifdef ZPQ_DUO_ROTATE   // experiment: one warp of each role per SM sub-partition instead of one role per sub-partition
+  const int pair = warp / W, role = warp == nwarps - 1 ? 4 : (warp + pair) % W;
+#else
   const int pair = warp / W, role = warp == nwarps - 1 ? 4 : warp % W;
+#endif
   // The order of the role bodies in the kernel image is a tuning knob: the hot loops of the five roles together are about
   // as large as the SM's 32 KB instruction cache, and which of them collide depends on their addresses.
   constexpr int O0 = ZPQ_DUO_ORDER / 10000 % 10, O1 = ZPQ_DUO_ORDER / 1000 % 10, O2 = ZPQ_DUO_ORDER / 100 % 10,
