@@ -127,4 +127,129 @@ namespace ZPAQSharp
             }
         }
     }
+    /// <summary>Replacement body of Compressor (Compressor.cs:12-304) over the batch ABI: same methods, same call order,
+    /// same bytes.  A segment is buffered and coded by the GPU in endSegment; one segment per block.  The Python model of
+    /// this class, zpaqsharp_b200/facade.py, is what the tests run (tests/test_facade_host.py, tests/test_gpu_facade.py).</summary>
+    public unsafe class CompressorB200
+    {
+        enum State { INIT, BLOCK1, SEG1, BLOCK2, SEG2 }
+        State state = State.INIT;
+        Writer output; Reader input;
+        byte[] hdr = new byte[0], pz = new byte[0], pcomp = new byte[0];
+        readonly System.IO.MemoryStream seg = new System.IO.MemoryStream();
+        static IntPtr ctx;
+        static IntPtr Ctx()
+        {
+            if (ctx == IntPtr.Zero && ZpaqB200Native.zpq_create(null, 0, out ctx) != 0)
+                LibZPAQ.error(Marshal.PtrToStringAnsi(ZpaqB200Native.zpq_last_error(IntPtr.Zero)));
+            return ctx;
+        }
+
+        public void setOutput(Writer o) { output = o; }
+        public void setInput(Reader i) { input = i; }
+
+        public void writeTag()                                   // Compressor.cs:27-43
+        {
+            foreach (byte b in new byte[] { 0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3 }) output.put(b);
+        }
+
+        public void startBlock(int level)                        // Compressor.cs:45-83
+        {
+            if (level < 1) LibZPAQ.error("compression level must be at least 1");
+            var buf = new byte[1024];
+            long n;
+            fixed (byte* p = buf) n = ZpaqB200Native.zpq_builtin_model(level, p, (ulong)buf.Length);
+            if (n < 0) LibZPAQ.error("compression level too high");
+            Array.Resize(ref buf, (int)n);
+            startBlock(buf);
+        }
+
+        public void startBlock(byte[] hcomp)                     // Compressor.cs:85-99
+        {
+            hdr = hcomp; pz = new byte[0];
+            output.put('z'); output.put('P'); output.put('Q');
+            output.put(1 + (hdr[6] == 0 ? 1 : 0));
+            output.put(1);
+            foreach (byte b in hdr) output.put(b);
+            state = State.BLOCK1;
+        }
+
+        public void startSegment(string filename = null, string comment = null)   // Compressor.cs:133-146
+        {
+            if (state == State.BLOCK2) LibZPAQ.error("the device path codes one segment per block");
+            output.put(1);
+            if (filename != null) foreach (char c in filename) output.put(c);
+            output.put(0);
+            if (comment != null) foreach (char c in comment) output.put(c);
+            output.put(0);
+            output.put(0);
+            seg.SetLength(0);
+            pcomp = new byte[0];
+            state = State.SEG1;
+        }
+
+        public void postProcess(byte[] program = null, int len = 0)               // Compressor.cs:156-190
+        {
+            if (state == State.SEG2) return;
+            if (program == null) pcomp = pz;
+            else if (len == 0) { len = program[0] + 256 * program[1]; pcomp = new byte[len]; Array.Copy(program, 2, pcomp, 0, len); }
+            else { pcomp = new byte[len]; Array.Copy(program, 0, pcomp, 0, len); }
+            state = State.SEG2;
+        }
+
+        public bool compress(int n = -1)                         // Compressor.cs:193-221
+        {
+            if (state == State.SEG1) postProcess();
+            const int BUFSIZE = 1 << 14;
+            var buf = new char[BUFSIZE];
+            while (n != 0)
+            {
+                int nbuf = BUFSIZE;
+                if (n >= 0 && n < nbuf) nbuf = n;
+                int nr = input.read(buf, nbuf);
+                if (nr < 0 || nr > BUFSIZE || nr > nbuf) LibZPAQ.error("invalid read size");
+                if (nr <= 0) return false;
+                if (n >= 0) n -= nr;
+                for (int i = 0; i < nr; ++i) seg.WriteByte((byte)buf[i]);
+            }
+            return true;
+        }
+
+        public void endSegment(byte[] sha1string = null)         // Compressor.cs:224-249
+        {
+            if (state == State.SEG1) postProcess();
+            byte[] data = seg.ToArray();
+            var off = new ulong[] { 0, (ulong)data.Length };
+            var outBuf = new byte[data.Length + data.Length / 4 + hdr.Length + pcomp.Length * 4 + 65536];
+            var outOff = new ulong[2];
+            var args = new int[9];
+            fixed (byte* ph = hdr, pp = pcomp, pi = data, po = outBuf)
+            fixed (ulong* poff = off, pooff = outOff)
+            fixed (int* pa = args)
+            {
+                int rc = ZpaqB200Native.zpq_compress_blocks_model(Ctx(), ph, (ulong)hdr.Length, pcomp.Length > 0 ? pp : null, (ulong)pcomp.Length, pa,
+                                                                  pi, poff, 1, null, null, 0, 0, po, (ulong)outBuf.Length, pooff);
+                if (rc != 0) LibZPAQ.error(Marshal.PtrToStringAnsi(ZpaqB200Native.zpq_last_error(ctx)));
+            }
+            // the library wrote "zPQ" level 1, the header and a segment header with its default comment (the decimal size)
+            // in front of the coded bytes, and 254 255 behind them; this class has written its own headers already
+            int skip = 5 + hdr.Length + 1 + 1 + data.Length.ToString().Length + 1 + 1;
+            int end = (int)outOff[1] - 2;                        // up to and including the four zero bytes
+            for (int i = skip; i < end; ++i) output.put(outBuf[i]);
+            if (sha1string != null)
+            {
+                output.put(253);
+                for (int i = 0; i < 20; ++i) output.put(sha1string[i]);
+            }
+            else
+                output.put(254);
+            state = State.BLOCK2;
+        }
+
+        public void endBlock()                                   // Compressor.cs:294-299
+        {
+            output.put(255);
+            state = State.INIT;
+        }
+    }
 }
