@@ -114,7 +114,13 @@ struct Lockstep {
   int lag = 0, spins = 0;
   // true: poll again (some recent straggler is not ready yet)
   __device__ __forceinline__ bool hold(bool running, bool ready) {
-    if (__any_sync(ZPQ_FULL, running && !ready && lag < kLagMax) && spins < kSpinMax) { ++spins; return true; }
+    if (__any_sync(ZPQ_FULL, running && !ready && lag < kLagMax) && spins < kSpinMax) {
+      ++spins;
+#ifdef ZPQ_DUO_SPIN_SLEEP   // experiment: a third of the executed warp instructions are these polls; a sleeping warp frees its issue slots
+      __nanosleep(ZPQ_DUO_SPIN_SLEEP);
+#endif
+      return true;
+    }
     spins = 0;
     lag = ready ? 0 : (running ? (lag < 255 ? lag + 1 : lag) : 0);
     return false;
