@@ -114,13 +114,7 @@ struct Lockstep {
   int lag = 0, spins = 0;
   // true: poll again (some recent straggler is not ready yet)
   __device__ __forceinline__ bool hold(bool running, bool ready) {
-    if (__any_sync(ZPQ_FULL, running && !ready && lag < kLagMax) && spins < kSpinMax) {
-      ++spins;
-#ifdef ZPQ_DUO_SPIN_SLEEP   // experiment: a third of the executed warp instructions are these polls; a sleeping warp frees its issue slots
-      __nanosleep(ZPQ_DUO_SPIN_SLEEP);
-#endif
-      return true;
-    }
+    if (__any_sync(ZPQ_FULL, running && !ready && lag < kLagMax) && spins < kSpinMax) { ++spins; return true; }
     spins = 0;
     lag = ready ? 0 : (running ? (lag < 255 ? lag + 1 : lag) : 0);
     return false;
@@ -1011,11 +1005,7 @@ __device__ __forceinline__ void encode_duo_body(const CodecParams& P, uint8_t* s
   stage_shared(P, smem, S);
   constexpr int W = DM::SPLIT ? 4 : 3;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#ifdef ZPQ_DUO_ROTATE   // experiment: one warp of each role per SM sub-partition instead of one role per sub-partition
-  const int pair = warp / W, role = warp == nwarps - 1 ? 4 : (warp + pair) % W;
-#else
   const int pair = warp / W, role = warp == nwarps - 1 ? 4 : warp % W;
-#endif
   // The order of the role bodies in the kernel image is a tuning knob: the hot loops of the five roles together are about
   // as large as the SM's 32 KB instruction cache, and which of them collide depends on their addresses.
   constexpr int O0 = ZPQ_DUO_ORDER / 10000 % 10, O1 = ZPQ_DUO_ORDER / 1000 % 10, O2 = ZPQ_DUO_ORDER / 100 % 10,
