@@ -628,11 +628,14 @@ def decompresser_text() -> str:
     (Decoder.cs:70), and the C#-ified signatures of findFilename / readComment / readSegmentEnd whose bodies still use the
     C++ parameter names (filename, comment, sha1string as a writable buffer).  Supplied by the harness because their C#
     text is not C++ any more: Decoder.get (unbuffered here), ZPAQL.outc (Decoder.cs:113-123, ZPAQL.cs:201-207: the
-    comma of libzpaq's `(outbuf[bufptr]=ch, ++bufptr==size)` became `&&`), ZPAQL.clear / initp (H and M are `hv` / `mv` here)."""
+    comma of libzpaq's `(outbuf[bufptr]=ch, ++bufptr==size)` became `&&`), ZPAQL.clear / initp (H and M are `hv` / `mv` here).
+    Also ZPAQL.memory / pow2 (ZPAQL.cs:58-81, 1306-1311) as they lie -> ref_block_memory."""
     base = compressor_text()
     fix = lambda t: re.sub(r"Array\.Resize\(ref\s+([\w\.]+),\s*", r"\1.resize(", t).replace(".Length", ".size()").replace("@", "")
     cs = lambda t: fix(t).replace("= null", "= 0")
     flush = cs(_method_text(ZPAQL_SRC, "void flush() // write outbuf"))
+    mem = cs(_method_text(ZPAQL_SRC, "double memory() // Return memory requirement in bytes"))
+    pw = _method_text(ZPAQL_SRC, "static double pow2(int x)")
     d_dec = cs(_method_text(DEC_SRC, "int decompress() // return a byte or EOF"))
     d_skip = cs(_method_text(DEC_SRC, "int skip() // skip to the end of the segment"))
     assert "\tnt c = -1;" in d_skip.replace("    ", "\t") or "nt c = -1;" in d_skip
@@ -655,12 +658,15 @@ def decompresser_text() -> str:
 """ + flush + r"""
   void clear() { cend = hbegin = hend = 0; a = b = c = d = 0; f = pc = 0; header.resize(0); hv.resize(0); mv.resize(0); memset(r, 0, sizeof r); }  // ZPAQL.cs:33-42
   void initp() { hv.resize(1, header[4]); mv.resize(1, header[5]); memset(r, 0, sizeof r); a = b = c = d = 0; f = 0; pc = 0; }   // ZPAQL.cs:52-56, 1010-1026
-  double memory() { return 0; }
+""" + mem + r"""
 """, 1)
     wref = "struct WriterRef { RefSink* s; WriterRef(RefSink* s_ = 0) : s(s_) {} void put(int c) { s->put(c & 255); }"
     assert base.count(wref) == 1
     base = base.replace(wref, wref + " explicit operator bool() const { return s != 0; }", 1)
     base = base.replace("struct RefVM {", "struct ShaRef { explicit operator bool() const { return false; } void write(const char*, int) {} };\nstruct RefVM {", 1)
+    en = "enum { NONE, CONS, CM, ICM, MATCH, AVG, MIX2, MIX, ISSE, SSE };\n"
+    assert base.count(en) == 1
+    base = base.replace(en, "", 1).replace("struct ShaRef {", en + pw + "\nstruct ShaRef {", 1)
     return base + r"""
 struct RefDecoder : Reader {                           // Decoder.cs:16-159: decompress, skip, init, decode are reference text
   ReaderRef in; uint low, high, curr; RefPredictorN pr;
@@ -685,6 +691,11 @@ struct RefDecompresser {
 };
 // LibZPAQ.decompress (LibZPAQ.cs:65-79): every segment of every block of `arc` into `out`; per segment 21 bytes into
 // `marks` (readSegmentEnd: 0 = no checksum, else 1 + the stored SHA-1).  Returns bytes written, -1 on a reference error.
+// ZPAQL.memory() (ZPAQL.cs:58-81) of a block header as stored in an archive (read by ZPAQL.read).
+extern "C" double ref_block_memory(const unsigned char* hdr) {
+  try { RefVM* v = new RefVM(); v->rcode = 0; v->rcode_size = 0; MemoryReader m((const char*)hdr, 0); v->read(&m); double r = v->memory(); delete v; return r; }
+  catch (const std::exception&) { return -1; }
+}
 extern "C" long long ref_decompress(const unsigned char* arc, unsigned long long n, unsigned char* out, unsigned long long cap,
                                     unsigned char* marks, int max_segs, int* nsegs) {
   *nsegs = 0;

@@ -93,3 +93,21 @@ def test_reference_decoder_rejects_a_damaged_stream(ref):
         assert got != data or st[0] != 1
     except po.OracleError:
         pass
+
+
+@pytest.mark.parametrize("what", [("level", 1), ("level", 2), ("level", 3), ("method", "x0,0c256,0,255,255"), ("method", "x4,3ci1"),
+                                  ("method", "x0,0c1,0,255,255a24mm16ts19t0w2"), ("method", "x6,1,4,0,3,24"), ("method", "0")],
+                         ids=lambda w: str(w[1]))
+def test_block_memory_matches_reference_zpaql_memory(ref, what):
+    # ZPAQL.memory() (ZPAQL.cs:58-81) as it lies, on the header as ZPAQL.read parses it; mid.cfg: 111,424,926
+    from oracle import frontend
+    from zpaqsharp_b200 import libzpaq as z
+    hdr = bytes(frontend.builtin_model(what[1])[0]) if what[0] == "level" else bytes(frontend.plan_block(what[1], b"x" * 1000)["hdr"])
+    ref.ref_block_memory.argtypes = [C.c_char_p]
+    ref.ref_block_memory.restype = C.c_double
+    want = ref.ref_block_memory(hdr)
+    assert want > 0
+    assert po.block_memory(hdr) == want
+    assert z.block_memory(hdr) == want                      # the product's host code (no GPU needed)
+    if what == ("level", 2):
+        assert int(want) == 111424926
