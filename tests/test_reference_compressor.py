@@ -92,3 +92,25 @@ def test_stored_mode_chunks_of_64k(ref):
     want = po.compress_block(data, "0")
     got = _ref_block(ref, 0, bytes(plan["hdr"]), b"", None, plan["comment"].encode(), data, po.sha1(data))
     assert got == want
+
+
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_archives.json")))
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
+def test_committed_golden_archives_are_what_the_reference_text_writes(ref, case):
+    # tests/golden/oracle_archives.json (made by tests/golden/make_archives.py with the oracle) is what the GPU tests decode
+    # and reproduce on the box, where /root/reference does not exist: every fixture must be exactly what the reference's
+    # Compressor text writes for that input (the model header from the front end, the payload pre-processed as
+    # LibZPAQ.compressBlock does before it hands the data over).
+    import base64
+    n = case["nbytes"]
+    data = synth.blocks(case["kind"], case["first_block"], 1, max(n, 1)).tobytes()[:n] if n else b""
+    golden = base64.b64decode(case["archive_b64"])
+    if case["how"] == "level":
+        got = _ref_block(ref, case["arg"], None, b"", None, str(len(data)).encode(), data, po.sha1(data))
+    else:
+        plan = frontend.plan_block(case["arg"], data)
+        payload = po.preprocess(data, plan["args"]) if plan["pcomp"] else data
+        got = _ref_block(ref, 0, bytes(plan["hdr"]), bytes(plan["pcomp"]), None, plan["comment"].encode(), payload, po.sha1(data))
+    assert got == golden
