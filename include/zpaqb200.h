@@ -176,6 +176,7 @@ typedef struct zpq_stats {
   uint32_t resident_blocks;                    /* blocks coded concurrently */
   uint64_t state_bytes_per_block;
   char kernel[96];                             /* which coding kernel ran: "lanes/aot2 (HCOMP compiled)", "lanes/nvrtc", ... */
+  double post_kernel_ms;                       /* decode: the post-processing pass (PostProcessor.cs:37-86) behind the decoding kernel */
 } zpq_stats;
 int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out);
 

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <condition_variable>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -30,7 +31,7 @@ bool find_spec_kernels(const Header& hdr, uint32_t smem_limit, SpecKernels& out,
 void spec_set_smem_limit(uint32_t bytes);
 Bytes nvrtc_compile(const std::string& src);
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
-                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g);
+                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g, bool* fdec);
 }
 
 using namespace zpq;
@@ -95,7 +96,7 @@ struct Device {
   uint32_t smem_optin = 0;
   Tables* d_tab = nullptr;
   DevBuf arena, in, work, pre, slots, out, meta, plan;
-  Timer t_all, t_h2d, t_kern, t_codec, t_d2h;
+  Timer t_all, t_h2d, t_kern, t_codec, t_d2h, t_post;
   zpq_stats stats{};
 
   void init(int dev) {
@@ -112,13 +113,13 @@ struct Device {
     build_tables(*t);
     CU(cudaMalloc(&d_tab, sizeof(Tables)));
     CU(cudaMemcpy(d_tab, t.get(), sizeof(Tables), cudaMemcpyHostToDevice));
-    t_all.init(); t_h2d.init(); t_kern.init(); t_codec.init(); t_d2h.init();
+    t_all.init(); t_h2d.init(); t_kern.init(); t_codec.init(); t_d2h.init(); t_post.init();
   }
   void fini() {
     cudaSetDevice(id);
     arena.release(); in.release(); work.release(); pre.release(); slots.release(); out.release(); meta.release(); plan.release();
     if (d_tab) cudaFree(d_tab);
-    t_all.fini(); t_h2d.fini(); t_kern.fini(); t_codec.fini(); t_d2h.fini();
+    t_all.fini(); t_h2d.fini(); t_kern.fini(); t_codec.fini(); t_d2h.fini(); t_post.fini();
     if (own) cudaStreamDestroy(own);
   }
 };
@@ -140,6 +141,7 @@ struct Launch {
   bool has_spec = false;
   bool skewed = false;     // encode with the time-skewed kernel (zpq_pipe.cuh)
   bool duo = false;        // encode with the two-role kernel (zpq_duo.cuh)
+  bool fast = false;       // decode with the speculative kernel (zpq_fdec.cuh); the post-processor is a separate pass
   uint32_t wb = 0;         // ... blocks per CTA
   uint32_t duo_roles = 3;  // ... role warps per block group (context, history, coder[, mixer])
   std::string kernel;      // what will run (for zpq_stats)
@@ -148,7 +150,10 @@ struct Launch {
 cudaError_t launch_codec(const Launch& L, const CodecParams& p, bool decode, cudaStream_t s) {
   if (L.has_spec) {
     void* args[] = {const_cast<CodecParams*>(&p)};
-    const void* k = decode ? L.spec.dec : L.duo ? L.spec.enc_duo : (L.skewed ? L.spec.enc : L.spec.enc_lanes);
+    const void* k = decode ? (L.fast ? L.spec.dec_fast : L.spec.dec) : L.duo ? L.spec.enc_duo : (L.skewed ? L.spec.enc : L.spec.enc_lanes);
+    // the dynamic shared memory limit is a per-device attribute (NVRTC kernels are shared by all devices of the process)
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sm.total);
+    if (e != cudaSuccess) return e;
     return cudaLaunchKernel(k, dim3(L.geom.grid), dim3(L.geom.warps_per_cta * 32), args, p.sm.total, s);
   }
   return decode ? launch_decode(p, L.geom, s) : launch_encode(p, L.geom, s);
@@ -170,10 +175,10 @@ uint32_t common_smem(const Plan& pl, SmemLayout& L) {
 bool force_generic();
 
 void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint64_t mem_for_arenas, uint32_t max_resident,
-                 Launch& L, bool want_skew = false, bool want_duo = false) {
+                 Launch& L, bool want_skew = false, bool want_duo = false, bool want_fast = false) {
   L.plan.reset(new Plan);
   build_plan(hdr, decode, 48 * 1024, *L.plan);
-  L.skewed = false; L.duo = false; L.wb = 0;
+  L.skewed = false; L.duo = false; L.wb = 0; L.fast = false;
   uint64_t fit = mem_for_arenas / std::max<uint64_t>(L.plan->arena_bytes, 1);
   if (fit < 1) throw Failure(ZPQ_E_NOMEM, "model state does not fit in device memory");
   uint64_t resident = std::min<uint64_t>({want, fit, (uint64_t)d.sms * 16});
@@ -217,6 +222,29 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
       L.kernel = std::string("duo/") + spec.origin + ", " + std::to_string(L.duo_roles) + " roles + coder warp, x" + std::to_string(B) + " blocks per warp";
       L.geom.grid = (uint32_t)((res + wb - 1) / wb);
       L.resident = (uint32_t)res;
+      return;
+    }
+    build_plan(hdr, decode, 48 * 1024, *L.plan);
+  }
+  if (want_fast && has_spec && spec.dec_fast && decode) {
+    // Speculative decoder (zpq_fdec.cuh): one warp per block, every ICM/ISSE map in the block's shared slice
+    for (uint32_t w = W; w >= 1 && !L.fast; --w) {
+      const uint32_t common = common_smem(*L.plan, L.sm);
+      const uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
+      build_plan(hdr, true, (avail / w) & ~127u, *L.plan, 0, true);
+      if (L.plan->pipe_maps && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.fast = true; W = w; }
+    }
+    if (L.fast) {
+      resident = std::min<uint64_t>(resident, (uint64_t)W * d.sms);
+      L.sm.slices = common_smem(*L.plan, L.sm);
+      L.sm.slice_bytes = L.plan->smem_warp_bytes;
+      L.sm.total = L.sm.slices + W * L.sm.slice_bytes;
+      L.geom.warps_per_cta = W;
+      L.geom.lanes = 1;
+      L.has_spec = true; L.spec = spec;
+      L.kernel = std::string("fdec/") + spec.origin + ", speculative, post-processor as a second pass";
+      L.geom.grid = (uint32_t)((resident + W - 1) / W);
+      L.resident = (uint32_t)resident;
       return;
     }
     build_plan(hdr, decode, 48 * 1024, *L.plan);
@@ -621,12 +649,17 @@ void compress_model(zpq_ctx* ctx, const Model& M, const uint8_t* in, const uint6
     for (uint32_t i = 0; i <= nb; ++i) out_off[first + i] = out_base + T.frame_off[i];
     return;
   }
-  // several devices: each compresses its range into its own device buffer, then the host copies
-  // the pieces to their final place once all sizes are known
+  // several devices: each compresses its range into its own device buffer and copies it to its final place as soon as
+  // the devices in front of it have reported their sizes (ordered reassembly through asynchronous copies: a device's
+  // D2H overlaps the kernels of the devices still running)
   std::vector<CompressTask> tasks(nd);
   std::vector<std::string> errs(nd);
   std::vector<int> codes(nd, 0);
   std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<int> done(nd, 0);
+  std::vector<uint64_t> totals(nd, 0);
   for (size_t k = 0; k < nd; ++k) {
     CompressTask& T = tasks[k];
     T.model = &M; T.h_in = in; T.in_off = in_off; T.first = cut[k]; T.count = cut[k + 1] - cut[k];
@@ -639,24 +672,29 @@ void compress_model(zpq_ctx* ctx, const Model& M, const uint8_t* in, const uint6
       try {
         if (tasks[k].count) compress_on_device(ctx, ctx->devs[k], tasks[k], nullptr, 0);
         else tasks[k].frame_off.assign(1, 0);
+        totals[k] = tasks[k].frame_off[tasks[k].count];
       } catch (const Failure& f) { codes[k] = f.code; errs[k] = f.what(); }
       catch (const std::exception& e) { codes[k] = ZPQ_E_CUDA; errs[k] = e.what(); }
+      uint64_t base = out_base;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        done[k] = 1;
+        cv.notify_all();
+        cv.wait(lk, [&]() { for (size_t j = 0; j < k; ++j) if (!done[j]) return false; return true; });
+        for (size_t j = 0; j < k; ++j) base += totals[j];
+      }
+      if (codes[k]) return;
+      const CompressTask& T = tasks[k];
+      for (uint32_t i = 0; i <= T.count; ++i) out_off[T.first + i] = base + T.frame_off[i];
+      if (base + totals[k] > out_cap) { codes[k] = ZPQ_E_OUTPUT; errs[k] = "output buffer too small"; return; }
+      Device& d = ctx->devs[k];
+      if (cudaSetDevice(d.id) != cudaSuccess || (totals[k] && cudaMemcpyAsync(out + base, d.out.p, totals[k], cudaMemcpyDeviceToHost, d.stream) != cudaSuccess) ||
+          cudaStreamSynchronize(d.stream) != cudaSuccess) { codes[k] = ZPQ_E_CUDA; errs[k] = "copy of the archive to the host failed"; }
+      d.stats.d2h_bytes = totals[k];
     });
   }
   for (auto& t : th) t.join();
   for (size_t k = 0; k < nd; ++k) if (codes[k]) throw Failure(codes[k], errs[k]);
-  uint64_t base = out_base;
-  for (size_t k = 0; k < nd; ++k) {
-    const CompressTask& T = tasks[k];
-    const uint64_t total = T.frame_off[T.count];
-    if (base + total > out_cap) throw Failure(ZPQ_E_OUTPUT, "output buffer too small");
-    Device& d = ctx->devs[k];
-    CU(cudaSetDevice(d.id));
-    if (total) CU(cudaMemcpyAsync(out + base, d.out.p, total, cudaMemcpyDeviceToHost, d.stream));
-    for (uint32_t i = 0; i <= T.count; ++i) out_off[T.first + i] = base + T.frame_off[i];
-    base += total;
-  }
-  for (size_t k = 0; k < nd; ++k) { CU(cudaSetDevice(ctx->devs[k].id)); CU(cudaStreamSynchronize(ctx->devs[k].stream)); }
 }
 
 void model_from_header_bytes(const uint8_t* hdr, uint64_t hdr_len, const uint8_t* pcomp, uint64_t pcomp_len, const int* args9,
@@ -679,16 +717,206 @@ struct DecBlock {
   bool hinted;
 };
 
-void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, uint8_t* out, uint64_t out_cap,
-                    uint64_t* out_off, uint8_t* sha1_status, uint8_t* block_status) {
-  Device& d = ctx->devs[0];
+// ZPQ_FDEC=0 keeps the lane-resident decoders with the post-processor inside (A/B measurements)
+bool want_fast_decode() { const char* e = getenv("ZPQ_FDEC"); return !(e && *e == '0'); }
+
+// Blocks [b0, b1) on one device: H2D of their archive bytes, decode (+ post-processing pass), SHA-1, ordered
+// compaction into d.out.  Fills lens / bstat / sha for these blocks; the caller copies d.out to the host.
+struct DecodeRange {
+  uint32_t b0 = 0, b1 = 0;
+  uint64_t total = 0;          // restored bytes of the range, gathered in d.out
+  std::string first_err;
+  bool any_corrupt = false;
+};
+
+void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, DecodeRange& R, const uint8_t* in, const uint64_t* in_off,
+                      std::vector<uint64_t>& lens, std::vector<uint8_t>& bstat, std::vector<uint8_t>& sha) {
   CU(cudaSetDevice(d.id));
   cudaStream_t s = d.stream;
   d.stats = zpq_stats{};
   d.t_all.start(s);
+  const uint32_t b0 = R.b0, b1 = R.b1, nbr = b1 - b0;
+  const uint64_t in_base = in_off[b0], in_total = in_off[b1] - in_off[b0];
+  reserve_io(d.in, in_total + 64, d.arena);
+  d.t_h2d.start(s);
+  if (in_total) CU(cudaMemcpyAsync(d.in.p, in + in_base, in_total, cudaMemcpyHostToDevice, s));
+  d.stats.h2d_bytes = in_total;
+  d.t_h2d.stop(s);
+
+  std::vector<BlockResult> res(nbr);
+  std::vector<uint32_t> pending;
+  for (uint32_t i = b0; i < b1; ++i) if (bstat[i] == ZPQ_BLOCK_OK) pending.push_back(i);
+  std::vector<uint64_t> slot_off(nbr + 1, 0);
+  uint32_t launches = 0;
+  double codec_ms = 0, post_ms = 0;
+  d.t_kern.start(s);
+  auto fail_block = [&](uint32_t i, uint8_t st, const std::string& why) {
+    bstat[i] = st; R.any_corrupt = true;
+    if (R.first_err.empty()) R.first_err = "block " + std::to_string(i) + ": " + why;
+  };
+  // Slots of finished blocks stay where they are; a block that outgrew its slot gets a larger one behind them and is
+  // decoded again (the size in a segment comment is only a first guess: the reference ignores comments, LibZPAQ.cs:65-79).
+  uint64_t slots_total = 0;
+  for (int attempt = 0; attempt < 8 && !pending.empty(); ++attempt) {
+    uint64_t need = slots_total;
+    for (uint32_t i : pending) { slot_off[i - b0] = need; need = align_up(need + blocks[i].cap, 16); }
+    if (need > d.slots.cap) {
+      // grow, keeping what finished blocks already hold
+      DevBuf bigger;
+      const uint64_t fr = free_device_memory();
+      if (need > fr + d.arena.cap) {
+        for (uint32_t i : pending) fail_block(i, ZPQ_BLOCK_OVERFLOW, "restored data does not fit in device memory");
+        pending.clear();
+        break;
+      }
+      try { bigger.reserve(need); }
+      catch (const Failure&) { cudaGetLastError(); d.arena.release(); bigger.reserve(need); }
+      if (slots_total) CU(cudaMemcpyAsync(bigger.p, d.slots.p, slots_total, cudaMemcpyDeviceToDevice, s));
+      CU(cudaStreamSynchronize(s));
+      d.slots.release();
+      d.slots = bigger; bigger.p = nullptr; bigger.cap = 0;
+    }
+    slots_total = need;
+    // group by header bytes
+    std::map<Bytes, std::vector<uint32_t>> groups;
+    for (uint32_t i : pending) groups[blocks[i].ref.hdr.wire].push_back(i);
+    for (auto& g : groups) {
+      const std::vector<uint32_t>& ids = g.second;
+      const Header& hdr = blocks[ids[0]].ref.hdr;
+      try {
+        std::vector<DecJob> jobs(ids.size());
+        std::vector<PostJob> pjobs(ids.size());
+        std::vector<DecSeg> segs;
+        Launch L;
+        const uint64_t fr = free_device_memory() + d.arena.cap;
+        const uint64_t reserve = 512ull << 20;
+        plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L, false, false, want_fast_decode());
+        uint64_t raw_total = 0;
+        for (size_t k = 0; k < ids.size(); ++k) {
+          const DecBlock& b = blocks[ids[k]];
+          jobs[k].seg_first = (uint32_t)segs.size();
+          jobs[k].seg_count = (uint32_t)b.ref.segs.size();
+          pjobs[k].out_off = slot_off[ids[k] - b0];
+          pjobs[k].out_cap = b.cap;
+          if (L.fast) {
+            // raw model stream: PCOMP preamble (<= 64 KB + 3) + transformed data (LZ77 output may exceed the data by 1/16)
+            jobs[k].out_off = raw_total; jobs[k].out_cap = b.cap + b.cap / 8 + 70000;
+            raw_total = align_up(raw_total + jobs[k].out_cap, 16);
+          } else { jobs[k].out_off = pjobs[k].out_off; jobs[k].out_cap = b.cap; }
+          for (const SegmentRef& sg : b.ref.segs) segs.push_back(DecSeg{b.start - in_base + sg.data_off, sg.data_len});
+        }
+        uint64_t mo = 0;
+        auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
+        const size_t nseg = std::max<size_t>(segs.size(), 1);
+        const uint64_t o_jobs = place(sizeof(DecJob) * jobs.size()), o_segs = place(sizeof(DecSeg) * nseg), o_send = place(8ull * nseg),
+                       o_pjobs = place(sizeof(PostJob) * jobs.size()), o_raw = place(sizeof(BlockResult) * jobs.size()),
+                       o_res = place(sizeof(BlockResult) * jobs.size()), o_queue = place(512);
+        d.meta.reserve(mo);
+        uint8_t* meta = d.meta.as<uint8_t>();
+        if (L.fast) reserve_io(d.work, std::max<uint64_t>(raw_total, 16), d.arena);
+        d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
+        d.plan.reserve(sizeof(Plan));
+        CU(cudaMemcpyAsync(d.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
+                           cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(meta + o_jobs, jobs.data(), sizeof(DecJob) * jobs.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(meta + o_pjobs, pjobs.data(), sizeof(PostJob) * jobs.size(), cudaMemcpyHostToDevice, s));
+        if (!segs.empty()) CU(cudaMemcpyAsync(meta + o_segs, segs.data(), sizeof(DecSeg) * segs.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(meta + o_queue, 0, 512, s));
+        CodecParams P{};
+        P.plan = d.plan.as<Plan>(); P.tab = d.d_tab;
+        P.arenas = d.arena.as<uint8_t>(); P.arena_stride = L.plan->arena_bytes;
+        P.in = d.in.as<uint8_t>(); P.out = L.fast ? d.work.as<uint8_t>() : d.slots.as<uint8_t>();
+        P.djobs = (const DecJob*)(meta + o_jobs); P.segs = (const DecSeg*)(meta + o_segs);
+        P.seg_end = (uint64_t*)(meta + o_send);
+        P.results = (BlockResult*)(meta + (L.fast ? o_raw : o_res));
+        P.njobs = (uint32_t)jobs.size(); P.resident = L.resident; P.queue = (uint32_t*)(meta + o_queue); P.sm = L.sm;
+        d.t_codec.start(s);
+        CU(launch_codec(L, P, true, s));
+        d.t_codec.stop(s);
+        ++launches;
+        if (L.fast) {
+          PostParams Q{};
+          Q.plan = d.plan.as<Plan>(); Q.arenas = d.arena.as<uint8_t>(); Q.arena_stride = L.plan->arena_bytes;
+          Q.raw = d.work.as<uint8_t>(); Q.djobs = P.djobs; Q.seg_end = P.seg_end; Q.raw_results = (const BlockResult*)(meta + o_raw);
+          Q.out = d.slots.as<uint8_t>(); Q.pjobs = (const PostJob*)(meta + o_pjobs); Q.results = (BlockResult*)(meta + o_res);
+          Q.njobs = P.njobs; Q.resident = L.resident; Q.queue = (uint32_t*)(meta + o_queue + 256);
+          d.t_post.start(s);
+          CU(launch_post(Q, s));
+          d.t_post.stop(s);
+          ++launches;
+        }
+        std::vector<BlockResult> r(jobs.size());
+        CU(cudaMemcpyAsync(r.data(), meta + o_res, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        codec_ms += d.t_codec.ms();
+        if (L.fast) post_ms += d.t_post.ms();
+        d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
+        snprintf(d.stats.kernel, sizeof d.stats.kernel, "%s", L.kernel.c_str());
+        for (size_t k = 0; k < ids.size(); ++k) res[ids[k] - b0] = r[k];
+      } catch (const Failure& f) {
+        // a header this build cannot run (or that does not fit) takes its own blocks down, not the batch
+        if (f.code == ZPQ_E_CUDA) throw;
+        cudaGetLastError();
+        for (uint32_t i : ids) { res[i - b0].status = ZPQ_BLOCK_CORRUPT; res[i - b0].out_len = 0; fail_block(i, ZPQ_BLOCK_CORRUPT, f.what()); }
+      }
+    }
+    std::vector<uint32_t> again;
+    for (uint32_t i : pending)
+      if (bstat[i] == ZPQ_BLOCK_OK && res[i - b0].status == ZPQ_BLOCK_OVERFLOW) { blocks[i].cap = blocks[i].cap * 8 + (1 << 20); again.push_back(i); }
+    pending.swap(again);
+  }
+  for (uint32_t i : pending) res[i - b0].status = ZPQ_BLOCK_OVERFLOW;
+  // ---- SHA-1 of every block's output when a checksum is stored (single-segment blocks) ----
+  for (uint32_t i = b0; i < b1; ++i) {
+    if (bstat[i] != ZPQ_BLOCK_OK) continue;
+    bstat[i] = (uint8_t)res[i - b0].status;
+    if (res[i - b0].status == ZPQ_BLOCK_OK) lens[i] = res[i - b0].out_len;
+    else fail_block(i, (uint8_t)res[i - b0].status, "failed to decode (status " + std::to_string(res[i - b0].status) + ")");
+  }
+  {
+    uint64_t mo = 0;
+    auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
+    const uint64_t o_slot = place(8ull * (nbr + 1)), o_len64 = place(8ull * nbr), o_len32 = place(4ull * nbr),
+                   o_foff = place(8ull * (nbr + 1)), o_dig = place(20ull * nbr);
+    d.meta.reserve(mo);
+    uint8_t* meta = d.meta.as<uint8_t>();
+    std::vector<uint32_t> len32(nbr);
+    std::vector<uint64_t> len64(nbr);
+    uint64_t max_len = 0, total = 0;
+    for (uint32_t i = 0; i < nbr; ++i) { len64[i] = lens[b0 + i]; len32[i] = (uint32_t)len64[i]; max_len = std::max(max_len, len64[i]); total += len64[i]; }
+    reserve_io(d.slots, 16, d.arena);
+    CU(cudaMemcpyAsync(meta + o_slot, slot_off.data(), 8ull * (nbr + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(meta + o_len64, len64.data(), 8ull * nbr, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(meta + o_len32, len32.data(), 4ull * nbr, cudaMemcpyHostToDevice, s));
+    CU(launch_sha1(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint32_t*)(meta + o_len32), nbr, meta + o_dig, s));
+    CU(launch_scan((const uint64_t*)(meta + o_len64), (uint64_t*)(meta + o_foff), nbr, s));
+    reserve_io(d.out, std::max<uint64_t>(total, 16), d.arena);
+    CU(launch_gather(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint64_t*)(meta + o_len64),
+                     d.out.as<uint8_t>(), (const uint64_t*)(meta + o_foff), d.out.cap, nbr, max_len, s));
+    launches += 3;
+    d.t_kern.stop(s);
+    std::vector<uint8_t> dig(20ull * nbr);
+    CU(cudaMemcpyAsync(dig.data(), meta + o_dig, 20ull * nbr, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < nbr; ++i) {
+      uint8_t st = 0;
+      const auto& segs = blocks[b0 + i].ref.segs;
+      if (bstat[b0 + i] == ZPQ_BLOCK_OK && segs.size() == 1 && segs[0].has_sha1)
+        st = memcmp(segs[0].sha1, &dig[20ull * i], 20) == 0 ? 1 : 2;
+      sha[b0 + i] = st;
+    }
+    R.total = total;
+  }
+  d.stats.kernel_ms = d.t_kern.ms(); d.stats.h2d_ms = d.t_h2d.ms();
+  d.stats.codec_kernel_ms = codec_ms; d.stats.post_kernel_ms = post_ms; d.stats.launches = launches;
+}
+
+void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, uint8_t* out, uint64_t out_cap,
+                    uint64_t* out_off, uint8_t* sha1_status, uint8_t* block_status) {
   // ---- parse framing on the host ----
   std::vector<DecBlock> blocks(nb);
-  std::vector<uint8_t> bstat(nb, ZPQ_BLOCK_OK);
+  std::vector<uint8_t> bstat(nb, ZPQ_BLOCK_OK), sha(nb, 0);
+  std::vector<uint64_t> lens(nb, 0);
   bool any_corrupt = false;
   std::string first_err;
   for (uint32_t i = 0; i < nb; ++i) {
@@ -703,145 +931,79 @@ void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
     }
     uint64_t cap = 0; b.hinted = true;
     for (const SegmentRef& sg : b.ref.segs) {
-      if (sg.size_hint >= 0) cap += (uint64_t)sg.size_hint;
-      else { b.hinted = false; cap += sg.data_len * 16 + (1 << 20); }
+      // the decimal size a comment starts with is a hint only (the reference ignores comments on decode):
+      // it is trusted as a first slot size while it is plausible for the coded bytes behind it
+      const uint64_t guess = sg.data_len * 16 + (1 << 20);
+      if (sg.size_hint >= 0 && (uint64_t)sg.size_hint <= std::max<uint64_t>(64ull << 20, sg.data_len * 4096)) cap += (uint64_t)sg.size_hint;
+      else { b.hinted = false; cap += guess; }
     }
     b.cap = cap + 16;
   }
-  const uint64_t in_base = in_off[0], in_total = in_off[nb] - in_off[0];
-  reserve_io(d.in, std::max<uint64_t>(in_total, 16), d.arena);
-  d.t_h2d.start(s);
-  if (in_total) CU(cudaMemcpyAsync(d.in.p, in + in_base, in_total, cudaMemcpyHostToDevice, s));
-  d.stats.h2d_bytes = in_total;
-  d.t_h2d.stop(s);
-
-  std::vector<BlockResult> res(nb);
-  std::vector<uint32_t> pending;
-  for (uint32_t i = 0; i < nb; ++i) if (bstat[i] == ZPQ_BLOCK_OK) pending.push_back(i);
-  std::vector<uint64_t> slot_off(nb + 1, 0);
-  std::vector<uint8_t> sha(nb, 0);
-  uint32_t launches = 0;
-  double codec_ms = 0;
-  d.t_kern.start(s);
-
-  for (int attempt = 0; attempt < 4 && !pending.empty(); ++attempt) {
-    // slots for the pending blocks
-    uint64_t slots_total = 0;
-    for (uint32_t i : pending) { slot_off[i] = slots_total; slots_total = align_up(slots_total + blocks[i].cap, 16); }
-    reserve_io(d.slots, std::max<uint64_t>(slots_total, 16), d.arena);
-    // group by header bytes
-    std::map<Bytes, std::vector<uint32_t>> groups;
-    for (uint32_t i : pending) groups[blocks[i].ref.hdr.wire].push_back(i);
-    std::vector<uint64_t> seg_end_all;  // per pending block & segment: output position at segment end
-    for (auto& g : groups) {
-      const std::vector<uint32_t>& ids = g.second;
-      const Header& hdr = blocks[ids[0]].ref.hdr;
-      std::vector<DecJob> jobs(ids.size());
-      std::vector<DecSeg> segs;
-      for (size_t k = 0; k < ids.size(); ++k) {
-        const DecBlock& b = blocks[ids[k]];
-        jobs[k].seg_first = (uint32_t)segs.size();
-        jobs[k].seg_count = (uint32_t)b.ref.segs.size();
-        jobs[k].out_off = slot_off[ids[k]];
-        jobs[k].out_cap = b.cap;
-        for (const SegmentRef& sg : b.ref.segs) segs.push_back(DecSeg{b.start - in_base + sg.data_off, sg.data_len});
-      }
-      uint64_t mo = 0;
-      auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
-      const uint64_t o_jobs = place(sizeof(DecJob) * jobs.size()), o_segs = place(sizeof(DecSeg) * std::max<size_t>(segs.size(), 1)),
-                     o_res = place(sizeof(BlockResult) * jobs.size()), o_queue = place(256);
-      d.meta.reserve(mo);
-      uint8_t* meta = d.meta.as<uint8_t>();
-      Launch L;
-      const uint64_t fr = free_device_memory() + d.arena.cap;
-      const uint64_t reserve = 512ull << 20;
-      plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L);
-      d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
-      d.plan.reserve(sizeof(Plan));
-      CU(cudaMemcpyAsync(d.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
-                         cudaMemcpyHostToDevice, s));
-      CU(cudaMemcpyAsync(meta + o_jobs, jobs.data(), sizeof(DecJob) * jobs.size(), cudaMemcpyHostToDevice, s));
-      if (!segs.empty()) CU(cudaMemcpyAsync(meta + o_segs, segs.data(), sizeof(DecSeg) * segs.size(), cudaMemcpyHostToDevice, s));
-      CU(cudaMemsetAsync(meta + o_queue, 0, 256, s));
-      CodecParams P{};
-      P.plan = d.plan.as<Plan>(); P.tab = d.d_tab;
-      P.arenas = d.arena.as<uint8_t>(); P.arena_stride = L.plan->arena_bytes;
-      P.in = d.in.as<uint8_t>(); P.out = d.slots.as<uint8_t>();
-      P.djobs = (const DecJob*)(meta + o_jobs); P.segs = (const DecSeg*)(meta + o_segs);
-      P.results = (BlockResult*)(meta + o_res);
-      P.njobs = (uint32_t)jobs.size(); P.resident = L.resident; P.queue = (uint32_t*)(meta + o_queue); P.sm = L.sm;
-      d.t_codec.start(s);
-      CU(launch_codec(L, P, true, s));
-      d.t_codec.stop(s);
-      ++launches;
-      std::vector<BlockResult> r(jobs.size());
-      CU(cudaMemcpyAsync(r.data(), meta + o_res, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
-      codec_ms += d.t_codec.ms();
-      d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
-      snprintf(d.stats.kernel, sizeof d.stats.kernel, "%s", L.kernel.c_str());
-      for (size_t k = 0; k < ids.size(); ++k) res[ids[k]] = r[k];
-    }
-    // an unhinted block that outgrew its slot gets a larger one and the batch is decoded again
-    bool again = false;
-    for (uint32_t i : pending)
-      if (res[i].status == ZPQ_BLOCK_OVERFLOW && !blocks[i].hinted) { blocks[i].cap *= 8; again = true; }
-    if (!again) break;
-  }
-  // ---- SHA-1 of every block's output when a checksum is stored (single-segment blocks) ----
-  std::vector<uint64_t> lens(nb, 0);
-  for (uint32_t i = 0; i < nb; ++i) {
-    if (bstat[i] != ZPQ_BLOCK_OK) continue;
-    bstat[i] = (uint8_t)res[i].status;
-    if (res[i].status == ZPQ_BLOCK_OK) lens[i] = res[i].out_len;
-    else { any_corrupt = true; if (first_err.empty()) first_err = "block " + std::to_string(i) + " failed to decode (status " + std::to_string(res[i].status) + ")"; }
-  }
+  // ---- partition over the devices by archive bytes, one host thread per device ----
+  const size_t nd = std::min<size_t>(ctx->devs.size(), std::max<uint32_t>(nb, 1));
+  std::vector<DecodeRange> ranges(nd);
   {
-    uint64_t mo = 0;
-    auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
-    const uint64_t o_slot = place(8ull * (nb + 1)), o_len64 = place(8ull * nb), o_len32 = place(4ull * nb),
-                   o_foff = place(8ull * (nb + 1)), o_dig = place(20ull * nb);
-    d.meta.reserve(mo);
-    uint8_t* meta = d.meta.as<uint8_t>();
-    std::vector<uint32_t> len32(nb);
-    uint64_t max_len = 0;
-    for (uint32_t i = 0; i < nb; ++i) { len32[i] = (uint32_t)lens[i]; max_len = std::max(max_len, lens[i]); }
-    CU(cudaMemcpyAsync(meta + o_slot, slot_off.data(), 8ull * (nb + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(meta + o_len64, lens.data(), 8ull * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(meta + o_len32, len32.data(), 4ull * nb, cudaMemcpyHostToDevice, s));
-    CU(launch_sha1(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint32_t*)(meta + o_len32), nb, meta + o_dig, s));
-    CU(launch_scan((const uint64_t*)(meta + o_len64), (uint64_t*)(meta + o_foff), nb, s));
-    uint64_t total = 0;
-    for (uint32_t i = 0; i < nb; ++i) total += lens[i];
-    reserve_io(d.out, std::max<uint64_t>(total, 16), d.arena);
-    CU(launch_gather(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint64_t*)(meta + o_len64),
-                     d.out.as<uint8_t>(), (const uint64_t*)(meta + o_foff), d.out.cap, nb, max_len, s));
-    launches += 3;
-    d.t_kern.stop(s);
-    std::vector<uint8_t> dig(20ull * nb);
-    d.t_d2h.start(s);
-    CU(cudaMemcpyAsync(dig.data(), meta + o_dig, 20ull * nb, cudaMemcpyDeviceToHost, s));
-    if (total > out_cap) { out_off[nb] = total; throw Failure(ZPQ_E_OUTPUT, "output buffer too small"); }
-    if (total) CU(cudaMemcpyAsync(out, d.out.p, total, cudaMemcpyDeviceToHost, s));
-    d.stats.d2h_bytes = total;
-    d.t_d2h.stop(s);
-    d.t_all.stop(s);
-    CU(cudaStreamSynchronize(s));
-    uint64_t acc = 0;
-    for (uint32_t i = 0; i < nb; ++i) {
-      out_off[i] = acc; acc += lens[i];
-      uint8_t st = 0;
-      const auto& segs = blocks[i].ref.segs;
-      if (bstat[i] == ZPQ_BLOCK_OK && segs.size() == 1 && segs[0].has_sha1)
-        st = memcmp(segs[0].sha1, &dig[20ull * i], 20) == 0 ? 1 : 2;
-      sha[i] = st;
+    const uint64_t total = in_off[nb] - in_off[0];
+    uint32_t b = 0;
+    for (size_t k = 0; k < nd; ++k) {
+      ranges[k].b0 = b;
+      if (k + 1 == nd) b = nb;
+      else { const uint64_t target = in_off[0] + total * (k + 1) / nd; while (b < nb && in_off[b + 1] <= target) ++b; }
+      ranges[k].b1 = b;
     }
-    out_off[nb] = acc;
   }
+  std::vector<std::string> errs(nd);
+  std::vector<int> codes(nd, 0);
+  // device k copies its restored bytes out as soon as devices 0..k-1 have reported their totals (ordered reassembly
+  // through asynchronous copies; no device waits for a slower one before starting its own kernels)
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<int> done(nd, 0);
+  bool too_small = false;
+  auto run = [&](size_t k) {
+    DecodeRange& R = ranges[k];
+    Device& d = ctx->devs[k];
+    try {
+      if (R.b1 > R.b0) decompress_range(ctx, d, blocks, R, in, in_off, lens, bstat, sha);
+    } catch (const Failure& f) { codes[k] = f.code; errs[k] = f.what(); }
+    catch (const std::exception& e) { codes[k] = ZPQ_E_CUDA; errs[k] = e.what(); }
+    uint64_t base = 0;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      done[k] = 1;
+      cv.notify_all();
+      cv.wait(lk, [&]() { for (size_t j = 0; j < k; ++j) if (!done[j]) return false; return true; });
+      for (size_t j = 0; j < k; ++j) base += ranges[j].total;
+    }
+    if (codes[k] || R.b1 == R.b0) return;
+    try {
+      cudaStream_t s = d.stream;
+      CU(cudaSetDevice(d.id));
+      d.t_d2h.start(s);
+      if (base + R.total > out_cap) { std::lock_guard<std::mutex> lk(mu); too_small = true; }
+      else if (R.total) CU(cudaMemcpyAsync(out + base, d.out.p, R.total, cudaMemcpyDeviceToHost, s));
+      d.stats.d2h_bytes = R.total;
+      d.t_d2h.stop(s);
+      d.t_all.stop(s);
+      CU(cudaStreamSynchronize(s));
+      d.stats.d2h_ms = d.t_d2h.ms(); d.stats.total_ms = d.t_all.ms();
+    } catch (const Failure& f) { codes[k] = f.code; errs[k] = f.what(); }
+  };
+  if (nd == 1) run(0);
+  else {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nd; ++k) th.emplace_back(run, k);
+    for (auto& t : th) t.join();
+  }
+  for (size_t k = 0; k < nd; ++k) if (codes[k]) throw Failure(codes[k], errs[k]);
+  uint64_t acc = 0;
+  for (uint32_t i = 0; i < nb; ++i) { out_off[i] = acc; acc += lens[i]; }
+  out_off[nb] = acc;
   if (sha1_status) memcpy(sha1_status, sha.data(), nb);
   if (block_status) memcpy(block_status, bstat.data(), nb);
-  d.stats.h2d_ms = d.t_h2d.ms(); d.stats.kernel_ms = d.t_kern.ms(); d.stats.d2h_ms = d.t_d2h.ms();
-  d.stats.total_ms = d.t_all.ms(); d.stats.codec_kernel_ms = codec_ms; d.stats.launches = launches;
+  if (too_small) throw Failure(ZPQ_E_OUTPUT, "output buffer too small");
+  for (size_t k = 0; k < nd; ++k)
+    if (ranges[k].any_corrupt) { any_corrupt = true; if (first_err.empty()) first_err = ranges[k].first_err; }
   if (any_corrupt) throw Failure(ZPQ_E_CORRUPT, first_err);
 }
 
@@ -1113,7 +1275,7 @@ int64_t zpq_specialize_model(const uint8_t* hdr, uint64_t hdr_len, char* source,
     Header h;
     parse_header(hdr, hdr_len, h);
     bool compiled = false;
-    src = generate_model_source(h, "Model_rt", "zpq_enc_rt", "zpq_dec_rt", &compiled, nullptr);
+    src = generate_model_source(h, "Model_rt", "zpq_enc_rt", "zpq_dec_rt", &compiled, nullptr, nullptr);
     Bytes cubin = nvrtc_compile(src);
     size = (int64_t)cubin.size();
     msg = compiled ? "HCOMP compiled" : "HCOMP interpreted";

@@ -152,7 +152,7 @@ std::string lane_test(uint32_t mask) {
 // Source of one specialised model.  `name` becomes the model struct name; the kernels are
 // extern "C" <enc_kernel> / <dec_kernel>.
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
-                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g) {
+                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g, bool* fdec) {
   std::unique_ptr<Plan> plp(new Plan);
   Plan& pl = *plp;
   build_plan(hdr, false, 48 * 1024, pl);
@@ -161,7 +161,7 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   o << "// Generated by zpq_codegen from block header";
   for (size_t i = 0; i < hdr.wire.size() && i < 48; ++i) { char b[8]; snprintf(b, sizeof b, " %02x", hdr.wire[i]); o << b; }
   o << (hdr.wire.size() > 48 ? " ...\n" : "\n");
-  o << "#include \"zpq_duo.cuh\"\nnamespace zpq {\nstruct " << name << " {\n";
+  o << "#include \"zpq_duo.cuh\"\n#include \"zpq_fdec.cuh\"\nnamespace zpq {\nstruct " << name << " {\n";
 
   uint32_t tmask[10] = {0};
   for (int i = 0; i < pl.n; ++i) tmask[pl.comp[i].type] |= 1u << i;
@@ -374,7 +374,63 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
     o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane, uint32_t smask) {\n"
       << "    return " << name << "::hcomp_m(S, W, vm, env, input, lane, smask);\n  }\n};\n";
   }
+  // ---- speculative decoder policy (zpq_fdec.cuh): every component evaluated redundantly in all lanes from the slots ----
+  bool fd = pl.n >= 1 && pl.n <= 8 && pl.nmix <= kMixRegs;
+  int ml = -1;
+  for (int i = 0; i < pl.n && fd; ++i) {
+    const int t = pl.comp[i].type;
+    if (t == C_MATCH) { if (ml >= 0) fd = false; ml = i; }
+    else if (t != C_CONS && t != C_CM && t != C_ICM && t != C_ISSE && t != C_MIX) fd = false;
+  }
+  for (int k = 0; k < pl.nmix && fd; ++k)
+    if (pl.mix[k].cmask != 255 || pl.mix[k].mask < 255 || pl.mix[k].m > 8) fd = false;
+  if (fdec) *fdec = fd;
+  if (fd) {
+    o << "struct Fdec_" << name << " {\n"
+      << "  static constexpr int N = " << pl.n << ", ML = " << ml << ", NMIX = " << pl.nmix << ";\n"
+      << "  static constexpr unsigned M_ICM = 0x" << std::hex << tmask[C_ICM] << "u, M_ISSE = 0x" << tmask[C_ISSE] << "u, M_CM = 0x" << tmask[C_CM]
+      << "u, M_CONS = 0x" << tmask[C_CONS] << std::dec << "u;\n";
+    for (int k = 0; k < pl.nmix; ++k)
+      o << "  typedef FMix<" << k << ", " << (int)pl.mix[k].lane << ", " << (int)pl.mix[k].j0 << ", " << (int)pl.mix[k].m << ", "
+        << (int)pl.mix[k].rate << ", " << pl.mix[k].mask << "u> FMix" << k << ";\n";
+    o << "  static __device__ __forceinline__ int eval(const Shared& S, LaneRegs& r, const int2* cw, int lane, int vmatch, int& pj, int* pin, int* pm) {\n";
+    int mk = 0;
+    for (int i = 0; i < pl.n; ++i) {
+      const CompDesc& d = pl.comp[i];
+      switch (d.type) {
+        case C_MATCH: o << "    const int v" << i << " = vmatch;\n"; break;
+        case C_ISSE: o << "    const int v" << i << " = clamp2k((cw[" << i << "].x * v" << (int)d.a[1] << " + cw[" << i << "].y) >> 16);\n"; break;
+        case C_MIX: {
+          o << "    int q" << i << " = 0;\n";
+          for (int j = 0; j < d.a[2]; ++j) o << "    q" << i << " = lane == " << j << " ? v" << (d.a[1] + j) << " : q" << i << ";\n";
+          o << "    pin[" << mk << "] = q" << i << "; pm[" << mk << "] = FMix" << mk << "::predict(r, lane, q" << i << ");\n"
+            << "    const int v" << i << " = pm[" << mk << "];\n";
+          ++mk;
+          break;
+        }
+        default: o << "    const int v" << i << " = cw[" << i << "].x;\n"; break;   // CONS, CM, ICM: the owner's published prediction
+      }
+    }
+    o << "    int own = 0; pj = 0;\n";
+    for (int i = 0; i < pl.n; ++i)
+      if (pl.comp[i].type == C_ISSE)
+        o << "    own = lane == " << i << " ? v" << i << " : own; pj = lane == " << i << " ? v" << (int)pl.comp[i].a[1] << " : pj;\n";
+    o << "    r.p = own;\n    return v" << (pl.n - 1) << ";\n  }\n";
+    o << "  static __device__ __forceinline__ void mix_new_byte(const Shared& S, WarpCtx& W, LaneRegs& r, int lane) {\n";
+    for (int k = 0; k < pl.nmix; ++k)
+      o << "    FMix" << k << "::new_byte(r, W, W.H[" << (int)pl.mix[k].lane << "u & W.hmask], lane);\n";
+    o << "  }\n";
+    o << "  template <int KB> static __device__ __forceinline__ void mix_advance(const Shared& S, LaneRegs& r, const WarpCtx& W, int lane, int y, int yprev, const int* pin, const int* pm, uint32_t c8new) {\n";
+    for (int k = 0; k < pl.nmix; ++k)
+      o << "    FMix" << k << "::template advance<KB>(S, r, W, lane, y, yprev, pin[" << k << "], pm[" << k << "], c8new);\n";
+    o << "  }\n";
+    o << "  static __device__ __forceinline__ int hcomp(const Shared& S, WarpCtx& W, VM& vm, VMEnv& env, uint32_t input, int lane) {\n"
+      << "    return " << name << "::hcomp(S, W, vm, env, input, lane);\n  }\n};\n";
+  }
   o << "}  // namespace zpq\n\n";
+  if (fd)
+    o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << dec_kernel << "_f(const zpq::CodecParams P) {\n"
+      << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::fdec_body<zpq::Fdec_" << name << ">(P, smem);\n}\n";
   if (duo)
     o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << enc_kernel << "_d(const zpq::CodecParams P) {\n"
       << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::encode_duo_body<zpq::Duo_" << name << ">(P, smem);\n}\n";
@@ -406,12 +462,13 @@ int main(int argc, char** argv) {
       const std::string id = "aot" + std::to_string(level);
       bool compiled = false;
       int duo_g = 0;
-      std::string src = zpq::generate_model_source(h, "Model_" + id, "zpq_enc_" + id, "zpq_dec_" + id, &compiled, &duo_g);
+      bool fd = false;
+      std::string src = zpq::generate_model_source(h, "Model_" + id, "zpq_enc_" + id, "zpq_dec_" + id, &compiled, &duo_g, &fd);
       std::ostringstream reg;
       reg << "\n#include \"zpq_aot.h\"\nnamespace {\nconst unsigned char kHeader[] = {";
       for (size_t i = 0; i < wire.size(); ++i) reg << (int)wire[i] << (i + 1 < wire.size() ? "," : "");
       reg << "};\nconst zpq::AotRegistrar kReg(kHeader, sizeof kHeader, (const void*)zpq_enc_" << id << ", (const void*)zpq_enc_" << id
-          << "_l, " << (duo_g ? "(const void*)zpq_enc_" + id + "_d" : std::string("nullptr")) << ", " << duo_g << ", (const void*)zpq_dec_" << id << ", \"" << id << (compiled ? " (HCOMP compiled)" : " (HCOMP interpreted)") << "\");\n}\n";
+          << "_l, " << (duo_g ? "(const void*)zpq_enc_" + id + "_d" : std::string("nullptr")) << ", " << duo_g << ", (const void*)zpq_dec_" << id << ", " << (fd ? "(const void*)zpq_dec_" + id + "_f" : std::string("nullptr")) << ", \"" << id << (compiled ? " (HCOMP compiled)" : " (HCOMP interpreted)") << "\");\n}\n";
       const std::string path = std::string(argv[1]) + "/zpq_gen_" + id + ".cu";
       FILE* f = fopen(path.c_str(), "w");
       if (!f) { perror(path.c_str()); return 1; }

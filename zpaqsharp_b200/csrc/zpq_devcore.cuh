@@ -195,6 +195,7 @@ __device__ __forceinline__ void init_block_state(const Plan* plan, const Tables*
       const uint64_t nw = op.bytes >> 2;
       if (op.kind == 1) { for (uint64_t i = lane; i < nw; i += 32) q[i] = (i & 1) ? 0u : tab->icm_init[(i >> 1) & 255]; }
       else if (op.kind == 2) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->isse_init[i & 511]; }
+      else if (op.kind == 4) { for (uint64_t i = lane; i < nw; i += 32) q[i] = tab->icm_init[i & 255]; }
       else {
         const uint32_t w = tab->sse_init[lane] | op.value;  // period 32 == warp width
         for (uint64_t i = lane; i < nw; i += 32) q[i] = w;
@@ -821,6 +822,7 @@ __device__ __forceinline__ void decode_lanes_body(const CodecParams& P, uint8_t*
       }
     };
 
+    uint32_t low = 1, high = 0xFFFFFFFFu, curr = 0;     // Decoder.init: once per block (Decompresser.cs:128-134), not per segment
     for (uint32_t sg = 0; sg < J.seg_count && status == BLK_OK; ++sg) {
       const DecSeg seg = P.segs[J.seg_first + sg];
       const uint8_t* in = P.in + seg.in_off;
@@ -830,8 +832,8 @@ __device__ __forceinline__ void decode_lanes_body(const CodecParams& P, uint8_t*
         status = BLK_CORRUPT;
         return 0;
       };
-      uint32_t low = 1, high = 0xFFFFFFFFu, curr = 0;
-      for (int k = 0; k < 4; ++k) curr = curr << 8 | get();
+      if (curr == 0)                                      // segment initialisation, Decoder.cs:38-42
+        for (int k = 0; k < 4; ++k) curr = curr << 8 | get();
 #define ZPQ_DECODE(pr, y)                                                         \
       {                                                                           \
         if (curr < low || curr > high) status = BLK_CORRUPT;                      \

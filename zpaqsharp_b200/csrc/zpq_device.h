@@ -40,6 +40,9 @@ cudaError_t launch_scan(const uint64_t* len, uint64_t* off, uint32_t nb, cudaStr
 cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const uint64_t* len, uint8_t* dst,
                           const uint64_t* dst_off, uint64_t dst_cap, uint32_t nb, uint64_t max_len, cudaStream_t s);
 
+// Post-processing pass behind the speculative decoder: PostProcessor.write over every job's raw model stream.
+cudaError_t launch_post(const PostParams& q, cudaStream_t s);
+
 // ---- pre-processing (zpq_preproc.cu) ----
 size_t sa_workspace_bytes(uint64_t n_total);
 // Suffix arrays (block-local positions) and optionally inverse suffix arrays of every block of a

@@ -37,7 +37,8 @@ size_t parse_header(const uint8_t* p, size_t avail, Header& h);
 double header_memory(const Header& h);  // ZPAQL.memory(), ZPAQL.cs:58-81
 // Build the device plan.  smem_budget = shared bytes one resident block may use for its slice.
 // duo_g != 0 lays the shared slice out for the two-role encoder (zpq_duo.cuh) with duo_g lanes per block.
-void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& plan, int duo_g = 0);
+// fdec lays it out for the speculative decoder (zpq_fdec.cuh).
+void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& plan, int duo_g = 0, bool fdec = false);
 void build_tables(Tables& t);           // throws if the squash/stretch checksums are off
 void sha1_host(const uint8_t* p, uint64_t n, uint8_t out[20]);
 

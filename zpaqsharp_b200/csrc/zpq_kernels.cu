@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParam
       }
     };
 
+    uint32_t low = 1, high = 0xFFFFFFFFu, curr = 0;     // Decoder.init: once per block (Decompresser.cs:128-134), not per segment
     for (uint32_t sg = 0; sg < J.seg_count && status == ZPQ_BLOCK_OK; ++sg) {
       const DecSeg seg = P.segs[J.seg_first + sg];
       const uint8_t* in = P.in + seg.in_off;
@@ -434,8 +435,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParam
         if (status == ZPQ_BLOCK_OK) post(-1);
         continue;
       }
-      uint32_t low = 1, high = 0xFFFFFFFFu, curr = 0;
-      for (int k = 0; k < 4; ++k) curr = curr << 8 | get();
+      if (curr == 0)                                      // segment initialisation, Decoder.cs:38-42
+        for (int k = 0; k < 4; ++k) curr = curr << 8 | get();
       // decode one bit with P(1) = pr/65536 (Decoder.cs:136-158)
 #define ZPQ_DECODE(pr, y)                                                         \
       {                                                                           \
@@ -637,6 +638,95 @@ cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const uin
   if (!nb || !max_len) return cudaSuccess;
   dim3 grid(nb, (unsigned)((max_len + kGatherChunk - 1) / kGatherChunk));
   k_gather<<<grid, 256, 0, s>>>(src, src_off, len, dst, dst_off, dst_cap);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Post-processing pass behind the speculative decoder (zpq_fdec.cuh): PostProcessor.write (PostProcessor.cs:37-86)
+// over the raw model stream of a block -- first byte 0 = PASS (copy), 1 = PROG (length, PCOMP program, then run the
+// program once per byte and once with 0xFFFFFFFF at the end of every segment).  One warp per resident arena (the PCOMP
+// arrays H, M, R live there; the model tables in it are dead by now), jobs from an atomic queue.  Programs makeConfig
+// emits are recognised by the host and run as native kernels instead (k_post_*); this kernel is the general case.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_post(const PostParams Q) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= Q.resident) return;
+  const Plan* plan = Q.plan;
+  uint8_t* arena = Q.arenas + (uint64_t)gw * Q.arena_stride;
+  for (;;) {
+    uint32_t job = 0;
+    if (lane == 0) job = atomicAdd(Q.queue, 1u);
+    job = __shfl_sync(FULL, job, 0);
+    if (job >= Q.njobs) break;
+    const DecJob J = Q.djobs[job];
+    const PostJob O = Q.pjobs[job];
+    const BlockResult R = Q.raw_results[job];
+    uint32_t status = R.status;
+    uint64_t opos = 0;
+    if (status == ZPQ_BLOCK_OK && J.seg_count) {
+      const uint8_t* raw = Q.raw + J.out_off;
+      uint8_t* out = Q.out + O.out_off;
+      const uint64_t* send = Q.seg_end + J.seg_first;
+      const uint64_t e0 = send[0];
+      if (e0 < 1) status = ZPQ_BLOCK_POSTPROC;                       // "Unexpected EOS"
+      else if (raw[0] == 0) {
+        // PASS: every byte behind the type byte, segment ends are no-ops
+        const uint64_t n = R.out_len - 1;
+        if (n > O.out_cap) status = ZPQ_BLOCK_OVERFLOW;
+        else for (uint64_t i = lane; i < n; i += 32) out[i] = raw[1 + i];
+        opos = n;
+      } else if (raw[0] == 1) {
+        uint32_t psize = 0;
+        if (e0 < 3) status = ZPQ_BLOCK_POSTPROC;
+        else {
+          psize = raw[1] + 256u * raw[2];
+          if (psize < 1 || 3ull + psize > e0) status = ZPQ_BLOCK_POSTPROC;   // "Empty PCOMP" / "Unexpected EOS"
+        }
+        if (status == ZPQ_BLOCK_OK) {
+          uint8_t* pcode = arena + plan->off_pcode;
+          for (uint32_t i = lane; i < psize + 3; i += 32) pcode[i] = i < psize ? raw[3 + i] : 0;
+          // ZPAQL.initp: H, M, R zeroed
+          uint32_t* H = reinterpret_cast<uint32_t*>(arena + plan->off_ph);
+          uint8_t* M = arena + plan->off_pm;
+          uint32_t* Rr = reinterpret_cast<uint32_t*>(arena + plan->off_pr);
+          const uint64_t hn = 1ull << plan->ph, mn4 = ((1ull << plan->pm) + 3) / 4;
+          for (uint64_t i = lane; i < hn; i += 32) H[i] = 0;
+          for (uint64_t i = lane; i < mn4; i += 32) reinterpret_cast<uint32_t*>(M)[i] = 0;
+          for (uint32_t i = lane; i < 256; i += 32) Rr[i] = 0;
+          __syncwarp();
+          if (lane == 0) {
+            VM pvm; pvm.b = pvm.c = pvm.d = pvm.f = 0;
+            VMEnv penv;
+            penv.code = pcode; penv.len = (int)psize;
+            penv.H = H; penv.hmask = (1u << plan->ph) - 1;
+            penv.M = M; penv.mmask = (uint32_t)((1ull << plan->pm) - 1);
+            penv.R = Rr;
+            penv.out = out; penv.out_pos = 0; penv.out_cap = O.out_cap;
+            uint64_t pos = 3ull + psize;
+            for (uint32_t sg = 0; sg < J.seg_count && status == ZPQ_BLOCK_OK; ++sg) {
+              const uint64_t end = send[sg];
+              const uint64_t budget = 65536 + 512 * (end + O.out_cap);
+              for (; pos < end; ++pos)
+                if (zpaql_run(pvm, penv, raw[pos], budget)) { status = ZPQ_BLOCK_ZPAQL; break; }
+              if (status == ZPQ_BLOCK_OK && zpaql_run(pvm, penv, 0xFFFFFFFFu, budget)) status = ZPQ_BLOCK_ZPAQL;
+            }
+            opos = penv.out_pos;
+          }
+          status = __shfl_sync(FULL, status, 0);
+          opos = __shfl_sync(FULL, (unsigned long long)opos, 0);
+          if (status == ZPQ_BLOCK_OK && opos > O.out_cap) status = ZPQ_BLOCK_OVERFLOW;
+        }
+      } else status = ZPQ_BLOCK_POSTPROC;                             // "unknown post processing type"
+    }
+    __syncwarp();
+    if (lane == 0) { Q.results[job].out_len = opos; Q.results[job].status = status; }
+  }
+}
+cudaError_t launch_post(const PostParams& q, cudaStream_t s) {
+  if (!q.njobs) return cudaSuccess;
+  const uint32_t warps = 8;
+  k_post<<<(q.resident + warps - 1) / warps, warps * 32, 0, s>>>(q);
   return cudaGetLastError();
 }
 

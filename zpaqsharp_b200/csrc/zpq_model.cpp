@@ -134,7 +134,7 @@ void build_tables(Tables& t) {
 }
 
 // ------------------------------------------------------------------------------------------
-void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl, int duo_g) {
+void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl, int duo_g, bool fdec) {
   memset(&pl, 0, sizeof(Plan) - sizeof(pl.hcomp));
   pl.n = h.n; pl.hh = h.hh; pl.hm = h.hm; pl.ph = h.ph; pl.pm = h.pm;
   if (h.hh > 28 || h.hm > 30 || h.ph > 28 || h.pm > 30)
@@ -157,7 +157,14 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
   auto stake = [&](uint32_t bytes) { uint32_t o = slice; slice = (uint32_t)align_up(slice + bytes, 16); return o; };
   const int nn = std::max(h.n, 1);
   pl.duo_g = duo_g;
-  if (duo_g) {
+  pl.fd_layout = fdec ? 1 : 0;
+  pl.smem_fd_cm = kNoSmem;
+  if (fdec) {
+    pl.smem_rows = stake(1024);   // 32 lanes x 16-byte hash row, twice (first nibble / candidates of the second)
+    pl.smem_chain = stake(512);   // 32 slots of {x0, y0, x1, y1}
+    const uint8_t* q = &h.wire[7];
+    for (int i = 0; i < h.n; ++i) { if (q[0] == C_CM && pl.smem_fd_cm == kNoSmem) pl.smem_fd_cm = stake(512); q += comp_len(q[0]); }
+  } else if (duo_g) {
     pl.smem_sync = stake(48);
     pl.smem_pfring = stake(128);
     pl.smem_rows = stake(32u * duo_g);   // duo_g lanes x 16-byte row cache, twice
@@ -165,7 +172,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
     pl.smem_p = stake(4u * nn);
     pl.smem_st = stake(20u * nn);
     pl.smem_rows = stake(1024);   // 32 lanes x 16-byte row cache, twice (the skewed encoder requests rows a nibble ahead)
-    pl.smem_chain = stake(256);
+    pl.smem_chain = stake(512);
   }
   // Pipelined encoder: component i works delay[i] bits behind the leading bit, strictly later than
   // everything it reads; a MIX additionally stays kPipeMixAhead bits back so that its weight rows
@@ -237,7 +244,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
       pl.ring_slots = 64; pl.ring_stride = (uint32_t)duo_g;
       pl.smem_pring = stake(2u * 64 * duo_g);
       pl.smem_hsnap = stake(4u * 8 * duo_g);
-    } else if (pl.pipe_ok) {
+    } else if (pl.pipe_ok && !fdec) {
       pl.smem_pring = stake(2u * pl.ring_slots * pl.ring_stride);
       pl.smem_bhring = stake(pl.ring_slots * pl.ring_stride);
       pl.smem_hsnap = stake(4u * 8 * pl.ring_stride);
@@ -277,7 +284,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (bits > 26) throw Failure(ZPQ_E_CONFIG, "max size for ICM is 26");
         d.mask = (uint32_t)((64ull << bits) - 16);
         d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false, 3);
-        if (duo_g) {   // the coder role owns ICM maps and addresses them with a 4-byte stride
+        if (duo_g || fdec) {   // the coder role owns ICM maps and addresses them with a 4-byte stride
           if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 4, 0, true, 1); }
           else { d.tab2 = take(1024); fill(d.tab2, 1024, 4, 0, false, 1); }
         } else if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 1, 0, true); }

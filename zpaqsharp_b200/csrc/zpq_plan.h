@@ -103,6 +103,9 @@ struct Plan {
   int32_t duo_split;            // 1: the MIX components run in a role warp of their own (no lane-owned component reads a MIX)
   uint32_t smem_sync;           // DuoSync words of the block
   uint32_t smem_pfring;         // int16 [64]: final stretched prediction per bit, for the arithmetic coder warp
+  // speculative decoder (zpq_fdec.cuh)
+  int32_t fd_layout;            // 1: the slice is laid out for it (rows, 32 slots of 16 bytes, compact ICM maps)
+  uint32_t smem_fd_cm;          // 8 x 64 bytes: the 16-entry line a CM component works on during a nibble, or kNoSmem
   MixDesc mix[kMaxMix];
   CompDesc comp[kMaxComp];
   uint8_t order[kMaxComp];      // components sorted by (level, coop)
@@ -127,7 +130,11 @@ struct DecSeg {         // one segment's coded byte range
 };
 struct DecJob {
   uint32_t seg_first, seg_count;  // into the DecSeg array
-  uint64_t out_off, out_cap;
+  uint64_t out_off, out_cap;      // restored bytes (decoders with the post-processor inside) or the raw model stream (zpq_fdec.cuh)
+};
+// Post-processing pass after the speculative decoder (PostProcessor.cs:37-86): raw model stream -> restored bytes.
+struct PostJob {
+  uint64_t out_off, out_cap;      // into the slot buffer of restored bytes
 };
 
 struct BlockResult {
@@ -172,7 +179,22 @@ struct CodecParams {
   uint32_t resident;          // warps that take part
   uint32_t* queue;            // next block index (atomic)
   uint32_t wb;                // two-role encoder: blocks per CTA
+  uint64_t* seg_end;          // speculative decoder: raw stream position at the end of every segment (parallel to segs)
   SmemLayout sm;
+};
+
+struct PostParams {
+  const Plan* plan;           // ph, pm and the PCOMP offsets inside an arena
+  uint8_t* arenas; uint64_t arena_stride;
+  const uint8_t* raw;         // what the decoder wrote: per job at djobs[j].out_off
+  const DecJob* djobs;
+  const uint64_t* seg_end;
+  const BlockResult* raw_results;
+  uint8_t* out;               // restored bytes: per job at pjobs[j].out_off
+  const PostJob* pjobs;
+  BlockResult* results;
+  uint32_t njobs, resident;
+  uint32_t* queue;
 };
 
 struct LaunchGeom {

@@ -17,7 +17,7 @@
 namespace zpq {
 
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
-                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g);
+                                  const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g, bool* fdec);
 
 namespace {
 
@@ -63,10 +63,10 @@ bool specialize_enabled() {
 }  // namespace
 
 AotRegistrar::AotRegistrar(const unsigned char* header, size_t len, const void* enc, const void* enc_lanes, const void* enc_duo, int duo_g,
-                           const void* dec, const char* origin) {
+                           const void* dec, const void* dec_fast, const char* origin) {
   Registry& r = registry();
   std::lock_guard<std::mutex> g(r.mu);
-  SpecKernels k; k.enc = enc; k.enc_lanes = enc_lanes; k.enc_duo = enc_duo; k.duo_g = duo_g; k.dec = dec; k.origin = origin;
+  SpecKernels k; k.enc = enc; k.enc_lanes = enc_lanes; k.enc_duo = enc_duo; k.duo_g = duo_g; k.dec = dec; k.dec_fast = dec_fast; k.origin = origin;
   r.table[Bytes(header, header + len)] = k;
 }
 
@@ -75,12 +75,12 @@ Bytes nvrtc_compile(const std::string& src) {
   Nvrtc& n = nvrtc();
   if (!n.ok) throw Failure(ZPQ_E_UNSUPPORTED, "libnvrtc is not available");
   nvrtcProgram prog = nullptr;
-  const char* hdr_src[4] = {kEmbedPlan, kEmbedDevcore, kEmbedPipe, kEmbedDuo};
-  const char* hdr_name[4] = {"zpq_plan.h", "zpq_devcore.cuh", "zpq_pipe.cuh", "zpq_duo.cuh"};
-  if (n.CreateProgram(&prog, src.c_str(), "zpq_model.cu", 4, hdr_src, hdr_name) != 0)
+  const char* hdr_src[5] = {kEmbedPlan, kEmbedDevcore, kEmbedPipe, kEmbedDuo, kEmbedFdec};
+  const char* hdr_name[5] = {"zpq_plan.h", "zpq_devcore.cuh", "zpq_pipe.cuh", "zpq_duo.cuh", "zpq_fdec.cuh"};
+  if (n.CreateProgram(&prog, src.c_str(), "zpq_model.cu", 5, hdr_src, hdr_name) != 0)
     throw Failure(ZPQ_E_CUDA, "nvrtcCreateProgram failed");
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
-  const int rc = n.CompileProgram(prog, 3, opts);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  const int rc = n.CompileProgram(prog, (int)(sizeof opts / sizeof opts[0]), opts);
   if (rc != 0) {
     size_t ls = 0;
     n.GetProgramLogSize(prog, &ls);
@@ -111,21 +111,23 @@ bool find_spec_kernels(const Header& hdr, uint32_t smem_limit, SpecKernels& out,
   if (e && *e == '0') { if (why_not) *why_not = "ZPQ_NVRTC=0"; return false; }
   try {
     int duo_g = 0;
-    std::string src = generate_model_source(hdr, "Model_rt", "zpq_enc_rt", "zpq_dec_rt", nullptr, &duo_g);
+    bool fd = false;
+    std::string src = generate_model_source(hdr, "Model_rt", "zpq_enc_rt", "zpq_dec_rt", nullptr, &duo_g, &fd);
     Bytes cubin = nvrtc_compile(src);
     cudaLibrary_t lib = nullptr;
     cudaError_t ce = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (ce != cudaSuccess) throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce));
-    cudaKernel_t ke = nullptr, kl = nullptr, kd = nullptr, kq = nullptr;
+    cudaKernel_t ke = nullptr, kl = nullptr, kd = nullptr, kq = nullptr, kf = nullptr;
     if ((ce = cudaLibraryGetKernel(&ke, lib, "zpq_enc_rt")) != cudaSuccess || (ce = cudaLibraryGetKernel(&kl, lib, "zpq_enc_rt_l")) != cudaSuccess ||
         (ce = cudaLibraryGetKernel(&kd, lib, "zpq_dec_rt")) != cudaSuccess)
       throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce));
     if (duo_g && (ce = cudaLibraryGetKernel(&kq, lib, "zpq_enc_rt_d")) != cudaSuccess)
       throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce));
-    for (cudaKernel_t k : {ke, kl, kd, kq})
-      if (k && (ce = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit)) != cudaSuccess)
-        throw Failure(ZPQ_E_CUDA, std::string("cudaFuncSetAttribute(nvrtc kernel): ") + cudaGetErrorString(ce));
-    SpecKernels k; k.enc = (const void*)ke; k.enc_lanes = (const void*)kl; k.enc_duo = (const void*)kq; k.duo_g = duo_g; k.dec = (const void*)kd; k.origin = "nvrtc";
+    if (fd && (ce = cudaLibraryGetKernel(&kf, lib, "zpq_dec_rt_f")) != cudaSuccess)
+      throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce));
+    // (the dynamic shared memory limit is a per-device attribute: launch_codec raises it on the device it launches on)
+    SpecKernels k; k.enc = (const void*)ke; k.enc_lanes = (const void*)kl; k.enc_duo = (const void*)kq; k.duo_g = duo_g; k.dec = (const void*)kd;
+    k.dec_fast = (const void*)kf; k.origin = "nvrtc";
     r.table[hdr.wire] = k;
     out = k;
     return true;
@@ -146,6 +148,7 @@ void spec_set_smem_limit(uint32_t bytes) {
     if (kv.second.enc_lanes) cudaFuncSetAttribute(kv.second.enc_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (kv.second.enc_duo) cudaFuncSetAttribute(kv.second.enc_duo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     cudaFuncSetAttribute(kv.second.dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (kv.second.dec_fast) cudaFuncSetAttribute(kv.second.dec_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   }
   cudaGetLastError();
 }

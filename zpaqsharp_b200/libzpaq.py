@@ -43,7 +43,7 @@ class Stats(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
                 ("codec_kernel_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches", C.c_uint32), ("resident_blocks", C.c_uint32), ("state_bytes_per_block", C.c_uint64),
-                ("kernel", C.c_char * 96)]
+                ("kernel", C.c_char * 96), ("post_kernel_ms", C.c_double)]
 
 
 _lib = None
