@@ -161,8 +161,11 @@ cudaError_t launch_codec(const Launch& L, const CodecParams& p, bool decode, cud
 
 uint32_t common_smem(const Plan& pl, SmemLayout& L) {
   uint32_t o = 0;
-  L.stretch = 0; L.squash = 65536; L.dt = 73728; L.dt2k = 77824; L.ns = 78336;
-  o = 79360;
+  bool with_dt = false;   // dt is only read by train() of CM and SSE components (Predictor.cs:1031-1036)
+  for (int i = 0; i < pl.n; ++i) with_dt = with_dt || pl.comp[i].type == C_CM || pl.comp[i].type == C_SSE;
+  L.stretch = 0; L.squash = 65536; L.dt2k = 73728; L.ns = 74240; L.dt = 75264;
+  L.tables_bytes = with_dt ? 79360u : 75264u;
+  o = L.tables_bytes;
   L.comp = o; o += (uint32_t)align_up((uint64_t)std::max(pl.n, 1) * sizeof(CompDesc), 16);
   L.order = o; o += (uint32_t)align_up(std::max(pl.n, 1), 16);
   L.steps = o; o += (uint32_t)align_up((uint64_t)std::max(pl.nsteps, 1) * sizeof(Step), 16);
@@ -228,11 +231,12 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
   }
   if (want_fast && has_spec && spec.dec_fast && decode) {
     // Speculative decoder (zpq_fdec.cuh): one warp per block, every ICM/ISSE map in the block's shared slice
-    for (uint32_t w = W; w >= 1 && !L.fast; --w) {
+    for (uint32_t w = std::min(W, 12u); w >= 1 && !L.fast; --w) {      // kFdecThreads = 384
       const uint32_t common = common_smem(*L.plan, L.sm);
       const uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
       build_plan(hdr, true, (avail / w) & ~127u, *L.plan, 0, true);
-      if (L.plan->pipe_maps && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.fast = true; W = w; }
+      const bool hm_ok = ((4ull << hdr.hh) > 2048 || L.plan->smem_h != kNoSmem) && ((1ull << hdr.hm) > 1024 || L.plan->smem_m != kNoSmem);
+      if (L.plan->pipe_maps && hm_ok && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.fast = true; W = w; }
     }
     if (L.fast) {
       resident = std::min<uint64_t>(resident, (uint64_t)W * d.sms);

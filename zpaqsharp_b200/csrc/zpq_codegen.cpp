@@ -388,12 +388,13 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   if (fd) {
     o << "struct Fdec_" << name << " {\n"
       << "  static constexpr int N = " << pl.n << ", ML = " << ml << ", NMIX = " << pl.nmix << ";\n"
+      << "  static constexpr bool H_SMEM = " << ((4ull << pl.hh) <= 2048 ? "true" : "false") << ", M_SMEM = " << ((1ull << pl.hm) <= 1024 ? "true" : "false") << ";\n"
       << "  static constexpr unsigned M_ICM = 0x" << std::hex << tmask[C_ICM] << "u, M_ISSE = 0x" << tmask[C_ISSE] << "u, M_CM = 0x" << tmask[C_CM]
-      << "u, M_CONS = 0x" << tmask[C_CONS] << std::dec << "u;\n";
+      << "u, M_CONS = 0x" << tmask[C_CONS] << ", M_SLOT = 0x" << (tmask[C_ICM] | tmask[C_ISSE] | tmask[C_CM] | tmask[C_CONS]) << std::dec << "u;\n";
     for (int k = 0; k < pl.nmix; ++k)
       o << "  typedef FMix<" << k << ", " << (int)pl.mix[k].lane << ", " << (int)pl.mix[k].j0 << ", " << (int)pl.mix[k].m << ", "
         << (int)pl.mix[k].rate << ", " << pl.mix[k].mask << "u> FMix" << k << ";\n";
-    o << "  static __device__ __forceinline__ int eval(const Shared& S, LaneRegs& r, const int2* cw, int lane, int vmatch, int& pj, int* pin, int* pm) {\n";
+    o << "  static __device__ __forceinline__ int eval(const Shared& S, LaneRegs& r, const int2* cw, const int* lm, int lane, int vmatch, int& pj, int* pin, int* pm) {\n";
     int mk = 0;
     for (int i = 0; i < pl.n; ++i) {
       const CompDesc& d = pl.comp[i];
@@ -401,8 +402,9 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
         case C_MATCH: o << "    const int v" << i << " = vmatch;\n"; break;
         case C_ISSE: o << "    const int v" << i << " = clamp2k((cw[" << i << "].x * v" << (int)d.a[1] << " + cw[" << i << "].y) >> 16);\n"; break;
         case C_MIX: {
-          o << "    int q" << i << " = 0;\n";
-          for (int j = 0; j < d.a[2]; ++j) o << "    q" << i << " = lane == " << j << " ? v" << (d.a[1] + j) << " : q" << i << ";\n";
+          o << "    const int q" << i << " = 0";
+          for (int j = 0; j < d.a[2]; ++j) o << " | (v" << (d.a[1] + j) << " & lm[" << j << "])";
+          o << ";\n";
           o << "    pin[" << mk << "] = q" << i << "; pm[" << mk << "] = FMix" << mk << "::predict(r, lane, q" << i << ");\n"
             << "    const int v" << i << " = pm[" << mk << "];\n";
           ++mk;
@@ -414,7 +416,7 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
     o << "    int own = 0; pj = 0;\n";
     for (int i = 0; i < pl.n; ++i)
       if (pl.comp[i].type == C_ISSE)
-        o << "    own = lane == " << i << " ? v" << i << " : own; pj = lane == " << i << " ? v" << (int)pl.comp[i].a[1] << " : pj;\n";
+        o << "    own |= v" << i << " & lm[" << i << "]; pj |= v" << (int)pl.comp[i].a[1] << " & lm[" << i << "];\n";
     o << "    r.p = own;\n    return v" << (pl.n - 1) << ";\n  }\n";
     o << "  static __device__ __forceinline__ void mix_new_byte(const Shared& S, WarpCtx& W, LaneRegs& r, int lane) {\n";
     for (int k = 0; k < pl.nmix; ++k)
@@ -429,7 +431,7 @@ std::string generate_model_source(const Header& hdr, const std::string& name, co
   }
   o << "}  // namespace zpq\n\n";
   if (fd)
-    o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << dec_kernel << "_f(const zpq::CodecParams P) {\n"
+    o << "extern \"C\" __global__ void __launch_bounds__(zpq::kFdecThreads, 1) " << dec_kernel << "_f(const zpq::CodecParams P) {\n"
       << "  extern __shared__ __align__(128) uint8_t smem[];\n  zpq::fdec_body<zpq::Fdec_" << name << ">(P, smem);\n}\n";
   if (duo)
     o << "extern \"C\" __global__ void __launch_bounds__(zpq::kCtaThreads, 1) " << enc_kernel << "_d(const zpq::CodecParams P) {\n"

@@ -210,10 +210,10 @@ __device__ __forceinline__ void init_block_state(const Plan* plan, const Tables*
 __device__ __forceinline__ void stage_shared(const CodecParams& P, uint8_t* smem, Shared& S) {
   const Plan* plan = P.plan;
   const SmemLayout& L = P.sm;
-  {  // stretch, squash, dt, dt2k, ns are the first 79360 bytes of Tables, in this order
+  {  // stretch, squash, dt2k, ns (and dt when the model trains a CM / SSE) are the first bytes of Tables, in this order
     const uint4* src = reinterpret_cast<const uint4*>(P.tab);
     uint4* dst = reinterpret_cast<uint4*>(smem + L.stretch);
-    for (int i = threadIdx.x; i < 79360 / 16; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(L.tables_bytes / 16); i += blockDim.x) dst[i] = src[i];
   }
   const int n = plan->n, ns = plan->nsteps;
   {

@@ -36,13 +36,33 @@
 
 namespace zpq {
 
+constexpr int kFdecThreads = 384;     // 12 warps per CTA at most: 170 registers per thread
+
+// Loads the compiler must issue where they are written (it otherwise sinks them behind the branches of the row choice and a
+// look-up becomes three dependent trips to HBM).  The addresses are global memory (arena tables).
+__device__ __forceinline__ uint4 fd_ldg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int fd_ldg32(const void* p) {
+  int v;
+  asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t fd_ldg8(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 // coded bytes of a segment, two bytes ahead of the decoder (Decoder.get, Decoder.cs:112-122); warp-uniform
 struct FdIn {
   const uint8_t* p;
-  uint64_t len, pos;
+  uint32_t len, pos;
   uint32_t n0, n1;
   __device__ __forceinline__ void open(const uint8_t* q, uint64_t l) {
-    p = q; len = l; pos = 0;
+    p = q; len = (uint32_t)l; pos = 0;
     n0 = l > 0 ? q[0] : 0u; n1 = l > 1 ? q[1] : 0u;
   }
   __device__ __forceinline__ uint32_t take(uint32_t& status) {
@@ -64,29 +84,28 @@ struct FMix {
     const uint32_t gl = (uint32_t)lane & 7u, grp = (uint32_t)lane >> 3, lo = gl < (uint32_t)M ? gl * 4u : 0u;
     W.mixh[K_] = hm;
     r.moff[K_] = rowoff(hm, 1u) + lo;
-    r.mw[K_] = *reinterpret_cast<const int*>(r.mixtab[K_] + r.moff[K_]);
-    r.mn0[K_] = *reinterpret_cast<const int*>(r.mixtab[K_] + rowoff(hm, 2u + (grp & 1u)) + lo);
-    r.mn1[K_] = *reinterpret_cast<const int*>(r.mixtab[K_] + rowoff(hm, 4u + grp) + lo);
+    r.mw[K_] = fd_ldg32(r.mixtab[K_] + r.moff[K_]);
+    r.mn0[K_] = fd_ldg32(r.mixtab[K_] + rowoff(hm, 2u + (grp & 1u)) + lo);
+    r.mn1[K_] = fd_ldg32(r.mixtab[K_] + rowoff(hm, 4u + grp) + lo);
   }
   static __device__ __forceinline__ int predict(const LaneRegs& r, int lane, int pin) {
     const int prod = lane < M ? (r.mw[K_] >> 8) * pin : 0;
     return clamp2k(__reduce_add_sync(ZPQ_FULL, prod) >> 8);
   }
-  // bit KB of the byte is decoded: train the row (c8 = the partial byte BEFORE this bit), move to the next one
+  // bit KB of the byte is decoded: train the row (nothing reads it again inside this byte), move to the next one
   template <int KB>
   static __device__ __forceinline__ void advance(const Shared& S, LaneRegs& r, const WarpCtx& W, int lane, int y, int yprev, int pin, int pm,
                                                  uint32_t c8new) {
-    const int sq = (int)S.squash[pm + 2048];
-    const int e0 = ((0 - sq) * RATE) >> 4, e1 = ((32767 - sq) * RATE) >> 4;
-    const int w0 = clamp512k(r.mw[K_] + ((e0 * pin + (1 << 12)) >> 13)), w1 = clamp512k(r.mw[K_] + ((e1 * pin + (1 << 12)) >> 13));
-    if (lane < M) *reinterpret_cast<int*>(const_cast<uint8_t*>(r.mixtab[K_]) + r.moff[K_]) = y ? w1 : w0;
+    const int err = ((y * 32767 - (int)S.squash[pm + 2048]) * RATE) >> 4;
+    const int w = clamp512k(r.mw[K_] + ((err * pin + (1 << 12)) >> 13));
+    if (lane < M) *reinterpret_cast<int*>(const_cast<uint8_t*>(r.mixtab[K_]) + r.moff[K_]) = w;
     if (KB < 7) {
       const uint32_t gl = (uint32_t)lane & 7u, grp = (uint32_t)lane >> 3, lo = gl < (uint32_t)M ? gl * 4u : 0u;
       const int g = KB == 0 ? y : 2 * yprev + y;
       r.mw[K_] = __shfl_sync(ZPQ_FULL, r.mn0[K_], (int)gl + 8 * g);
       r.moff[K_] = rowoff(W.mixh[K_], c8new) + lo;
       r.mn0[K_] = r.mn1[K_];
-      if (KB <= 4) r.mn1[K_] = *reinterpret_cast<const int*>(r.mixtab[K_] + rowoff(W.mixh[K_], c8new * 4u + grp) + lo);
+      if (KB <= 4) r.mn1[K_] = fd_ldg32(r.mixtab[K_] + rowoff(W.mixh[K_], c8new * 4u + grp) + lo);
     }
   }
 };
@@ -117,22 +136,20 @@ struct FdCtx {
 __device__ __forceinline__ void fd_find_issue(const LaneRegs& r, uint32_t cxt, uint4& f0, uint4& f1, uint4& f2, uint32_t& h0, uint32_t& chk) {
   chk = (cxt >> (r.a1 + 2)) & 255u;
   h0 = (cxt * 16u) & r.mask;
-  f0 = *reinterpret_cast<const uint4*>(r.tab + h0);
-  f1 = *reinterpret_cast<const uint4*>(r.tab + (h0 ^ 16u));
-  f2 = *reinterpret_cast<const uint4*>(r.tab + (h0 ^ 32u));
+  f0 = fd_ldg128(r.tab + h0);
+  f1 = fd_ldg128(r.tab + (h0 ^ 16u));
+  f2 = fd_ldg128(r.tab + (h0 ^ 32u));
 }
-// ... and pick: the row whose check byte matches, else the lowest-priority one, emptied
+// ... and pick: the row whose check byte matches, else the lowest-priority one, emptied.  Branch-free.
 __device__ __forceinline__ uint4 fd_find_pick(const uint4& f0, const uint4& f1, const uint4& f2, uint32_t h0, uint32_t chk, uint32_t& at) {
-  const uint32_t h1 = h0 ^ 16u, h2 = h0 ^ 32u;
-  uint4 v;
-  if ((f0.x & 255u) == chk) { v = f0; at = h0; }
-  else if ((f1.x & 255u) == chk) { v = f1; at = h1; }
-  else if ((f2.x & 255u) == chk) { v = f2; at = h2; }
-  else {
-    const uint32_t p0 = (f0.x >> 8) & 255u, p1 = (f1.x >> 8) & 255u, p2 = (f2.x >> 8) & 255u;
-    at = (p0 <= p1 && p0 <= p2) ? h0 : (p1 < p2 ? h1 : h2);
-    v = make_uint4(chk, 0u, 0u, 0u);
-  }
+  const bool m0 = (f0.x & 255u) == chk, m1 = (f1.x & 255u) == chk, m2 = (f2.x & 255u) == chk;
+  const uint32_t p0 = (f0.x >> 8) & 255u, p1 = (f1.x >> 8) & 255u, p2 = (f2.x >> 8) & 255u;
+  const uint32_t repl = (p0 <= p1 && p0 <= p2) ? 0u : (p1 < p2 ? 16u : 32u);
+  const bool hit = m0 || m1 || m2;
+  const uint32_t sel = m0 ? 0u : m1 ? 16u : m2 ? 32u : repl;
+  uint4 v = sel == 0u ? f0 : (sel == 16u ? f1 : f2);
+  if (!hit) v = make_uint4(chk, 0u, 0u, 0u);
+  at = h0 ^ sel;
   return v;
 }
 
@@ -147,10 +164,13 @@ struct FdLane {
   bool icm, isse, hashed, cm, cons;   // what this lane OWNS (lanes 0..7 only)
   bool hashedC;                       // component (lane & 7) is hashed (helper lanes mirror it)
   int consp;                          // CONS: its prediction (Predictor.cs:96-98)
-  uint32_t* map;                      // ICM map (4-byte stride) / ISSE map ({weight, bias} pairs) in the shared slice
+  const uint32_t* mapr;               // ICM / ISSE map in the shared slice, 8-byte entries ({p, -} / {weight, bias}); a readable dummy elsewhere
+  uint32_t* mapw;                     // the same for stores; lanes without a map write their own scratch words
+  uint32_t wmul;                      // 2 (words per entry) or 0
   uint8_t* rows0; uint8_t* rows1;     // the block's row buffers: 32 x 16 bytes each
   int4* slots;                        // 32 x {x0, y0, x1, y1}
   uint8_t* cmline;                    // CM: this lane's 16-entry line in shared memory
+  int lm[8];                          // lm[k] = lane == k ? -1 : 0
   // MATCH tables (warp-uniform)
   uint32_t* mtab; uint8_t* mbuf; uint32_t mmask, mmask2;
 };
@@ -173,13 +193,13 @@ __device__ __forceinline__ void fd_begin_byte(const Shared& S, FdCtx<FD>& X, con
   uint4 c0, c1, c2, c3;
   if (FD::M_CM) {
     cmbase = ((r.h ^ 1u) & r.mask) & ~15u;           // hmap4 == 1..15 in the first nibble: one 64-byte line (Predictor.cs:263-266)
-    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(r.tab) + cmbase);
-    c0 = q[0]; c1 = q[1]; c2 = q[2]; c3 = q[3];
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(r.tab) + cmbase;
+    c0 = fd_ldg128(q); c1 = fd_ldg128(q + 4); c2 = fd_ldg128(q + 8); c3 = fd_ldg128(q + 12);
   }
   if (FD::ML >= 0) {
     X.mh = X.W.H[FD::ML & X.W.hmask];
     const uint32_t slot = X.mh & L.mmask;
-    const uint32_t v = L.mtab[slot];
+    const uint32_t v = (uint32_t)fd_ldg32(L.mtab + slot);
     X.idxv = slot == X.lastslot ? X.lastpos : v;     // the slot written at the end of the last byte
     const int d2 = (int)S.dt2k[X.ma & 255u];
     X.mp0 = S.stretch[d2 & 32767];
@@ -187,13 +207,13 @@ __device__ __forceinline__ void fd_begin_byte(const Shared& S, FdCtx<FD>& X, con
   }
   const uint4 v = fd_find_pick(a0, a1, a2, h0, chk, at);
   uint8_t* slot0 = L.rows0 + lane * 16;
-  if (L.hashedC) *reinterpret_cast<uint4*>(slot0) = v;
+  *reinterpret_cast<uint4*>(slot0) = v;                      // (lanes without a hashed component keep garbage in their own slot)
   X.rowp = slot0; X.at = at;
   int plead = L.cons ? L.consp : 0;
   if (FD::M_ICM | FD::M_ISSE) {
     const uint32_t bh = (v.x >> 8) & 255u;
-    const uint32_t i0 = L.icm ? bh : bh * 2u;
-    if (L.hashed) { r.cxt = bh; r.t0 = (int)L.map[i0]; r.t1 = (int)L.map[L.isse ? i0 + 1u : i0]; }
+    const int2 e = *reinterpret_cast<const int2*>(L.mapr + bh * 2u);
+    if (FD::M_CM == 0 || L.hashed) { r.cxt = bh; r.t0 = e.x; r.t1 = e.y; }
     if (L.icm) plead = S.stretch[((uint32_t)r.t0 >> 8) & 32767u];
   }
   if (FD::M_CM) {
@@ -210,7 +230,8 @@ __device__ __forceinline__ void fd_begin_byte(const Shared& S, FdCtx<FD>& X, con
   L.slots[lane] = make_int4(s.x, s.y, s.x, s.y);
   __syncwarp();
 #pragma unroll
-  for (int q = 0; q < FD::N; ++q) { const int4 t = L.slots[q]; X.cw[q] = make_int2(t.x, t.y); }
+  for (int q = 0; q < FD::N; ++q)
+    if ((FD::M_SLOT >> q) & 1u) { const int4 t = L.slots[q]; X.cw[q] = make_int2(t.x, t.y); }
   X.yprev = 0;
 }
 
@@ -224,7 +245,7 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
 
   // ---- A: what bit K+1 will look at, under both outcomes of this bit ----
   uint32_t nb0 = 0, nb1 = 0;
-  int e0x = 0, e0y = 0, e1x = 0, e1y = 0;
+  int2 e0 = make_int2(0, 0), e1 = make_int2(0, 0);
   uint32_t ce0 = 0, ce1 = 0; int cm0 = 0, cm1 = 0;
   if (!BYTE_END) {
     if (FD::M_ICM | FD::M_ISSE) {
@@ -238,9 +259,8 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
         const uint8_t* base = L.rows1 + (gl + 16u * y2) * 16u;
         nb0 = base[1]; nb1 = base[8 * 16 + 1];
       }
-      const uint32_t a = L.icm ? nb0 : nb0 * 2u, b = L.icm ? nb1 : nb1 * 2u;
-      e0x = (int)L.map[a]; e0y = (int)L.map[L.isse ? a + 1u : a];
-      e1x = (int)L.map[b]; e1y = (int)L.map[L.isse ? b + 1u : b];
+      e0 = *reinterpret_cast<const int2*>(L.mapr + nb0 * 2u);
+      e1 = *reinterpret_cast<const int2*>(L.mapr + nb1 * 2u);
     }
     if (FD::M_CM) {
       if (!NIB_END) {
@@ -260,7 +280,7 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
     ek = (int)((X.mbyte >> (7 - K)) & 1u);
     vmatch = X.ma ? (ek ? X.mp1 : X.mp0) : 0;
   }
-  const int pf = FD::eval(S, r, X.cw, lane, vmatch, pj, pin, pm);     // sets r.p = this lane's own prediction
+  const int pf = FD::eval(S, r, X.cw, L.lm, lane, vmatch, pj, pin, pm);     // sets r.p = this lane's own prediction
   const uint32_t prf = (uint32_t)S.squash[pf + 2048] * 2u + 1u;
 
   // ---- C: this bit's map entry trained under both outcomes (Predictor.cs:375-381, 440-449; 365-373 for CM) ----
@@ -269,11 +289,14 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
   if (FD::M_ICM | FD::M_ISSE) {
     const int sq = (int)S.squash[r.p + 2048];
     const int er0 = 0 - sq, er1 = 32767 - sq;
-    const uint32_t pn = (uint32_t)r.t0;
-    const int i0 = (int)(pn + (uint32_t)(((int)(0 - (int)(pn >> 8))) >> 2));
-    const int i1 = (int)(pn + (uint32_t)(((int)(32767 - (int)(pn >> 8))) >> 2));
-    t0x = L.isse ? clamp512k(r.t0 + ((er0 * pj + (1 << 12)) >> 13)) : i0;
-    t1x = L.isse ? clamp512k(r.t0 + ((er1 * pj + (1 << 12)) >> 13)) : i1;
+    t0x = clamp512k(r.t0 + ((er0 * pj + (1 << 12)) >> 13));
+    t1x = clamp512k(r.t0 + ((er1 * pj + (1 << 12)) >> 13));
+    if (FD::M_ICM) {
+      const uint32_t pn = (uint32_t)r.t0;
+      const int i0 = (int)(pn + (uint32_t)(((int)(0 - (int)(pn >> 8))) >> 2));
+      const int i1 = (int)(pn + (uint32_t)(((int)(32767 - (int)(pn >> 8))) >> 2));
+      t0x = L.icm ? i0 : t0x; t1x = L.icm ? i1 : t1x;
+    }
     t0y = clamp512k(r.t1 + ((er0 + 16) >> 5));
     t1y = clamp512k(r.t1 + ((er1 + 16) >> 5));
     const uint32_t n16 = *reinterpret_cast<const uint16_t*>(S.ns + (r.cxt & 255u) * 4u);
@@ -294,8 +317,8 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
     int pl0 = L.cons ? L.consp : 0, pl1 = pl0;
     if (FD::M_ICM | FD::M_ISSE) {
       const bool s0 = nb0 == r.cxt, s1 = nb1 == r.cxt;
-      c0x = s0 ? t0x : e0x; c0y = s0 ? t0y : e0y;
-      c1x = s1 ? t1x : e1x; c1y = s1 ? t1y : e1y;
+      c0x = s0 ? t0x : e0.x; c0y = s0 ? t0y : e0.y;
+      c1x = s1 ? t1x : e1.x; c1y = s1 ? t1y : e1.y;
       if (FD::M_ICM) {
         const int q0 = S.stretch[((uint32_t)c0x >> 8) & 32767u], q1 = S.stretch[((uint32_t)c1x >> 8) & 32767u];
         if (L.icm) { pl0 = q0; pl1 = q1; }
@@ -315,7 +338,8 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
   int4 sl[FD::N];
   if (!BYTE_END) {
 #pragma unroll
-    for (int q = 0; q < FD::N; ++q) sl[q] = L.slots[q];
+    for (int q = 0; q < FD::N; ++q)
+      if ((FD::M_SLOT >> q) & 1u) sl[q] = L.slots[q];
   }
 
   // ---- E: the arithmetic decoder (Decoder.cs:136-158) ----
@@ -327,12 +351,9 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
 
   // ---- F: commit this bit, become bit K+1 ----
   if (FD::M_ICM | FD::M_ISSE) {
-    if (L.hashed) {
-      const uint32_t i0 = L.icm ? (r.cxt & 255u) : (r.cxt & 255u) * 2u;
-      L.map[i0] = (uint32_t)(y ? t1x : t0x);
-      if (L.isse) L.map[i0 + 1u] = (uint32_t)(y ? t1y : t0y);
-      X.rowp[(uint32_t)X.hmap4 & 15u] = (uint8_t)(y ? nx1 : nx0);
-    }
+    // lanes without a map store into their own scratch (entry 0 of their row slot)
+    *reinterpret_cast<int2*>(L.mapw + (r.cxt & 255u) * L.wmul) = make_int2(y ? t1x : t0x, y ? t1y : t0y);
+    X.rowp[(uint32_t)X.hmap4 & 15u] = (uint8_t)(y ? nx1 : nx0);
   }
   if (FD::M_CM) {
     if (L.cm) reinterpret_cast<uint32_t*>(L.cmline)[r.cxt] = (uint32_t)(y ? ct1 : ct0);
@@ -341,10 +362,11 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
   FD::template mix_advance<K>(S, r, X.W, lane, y, X.yprev, pin, pm, c8new);
   if (FD::ML >= 0) { if (ek != y) X.ma = 0; }
   if (!BYTE_END) {
-    if (L.hashed) { r.cxt = y ? nb1 : nb0; r.t0 = y ? c1x : c0x; r.t1 = y ? c1y : c0y; }
+    if (FD::M_ICM | FD::M_ISSE) { if (FD::M_CM == 0 || L.hashed) { r.cxt = y ? nb1 : nb0; r.t0 = y ? c1x : c0x; r.t1 = y ? c1y : c0y; } }
     if (FD::M_CM) { if (L.cm && !NIB_END) { r.cxt = y ? ce1 : ce0; r.t0 = y ? c1x : c0x; } }
 #pragma unroll
-    for (int q = 0; q < FD::N; ++q) X.cw[q] = y ? make_int2(sl[q].z, sl[q].w) : make_int2(sl[q].x, sl[q].y);
+    for (int q = 0; q < FD::N; ++q)
+      if ((FD::M_SLOT >> q) & 1u) X.cw[q] = y ? make_int2(sl[q].z, sl[q].w) : make_int2(sl[q].x, sl[q].y);
   }
   // Predictor.cs:463-474
   if (NIB_END) X.hmap4 = ((X.hmap4 & 0xf) << 5) | (y << 4) | 1;
@@ -369,14 +391,15 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
     if (K == 2) {
       uint32_t at = 0;
       const uint4 v = fd_find_pick(X.f0, X.f1, X.f2, X.fh0, X.fchk, at);
-      if (L.hashedC) *reinterpret_cast<uint4*>(L.rows1 + lane * 16) = v;
+      *reinterpret_cast<uint4*>(L.rows1 + lane * 16) = v;
       X.nat = at;
       __syncwarp();
     }
     if (NIB_END) {
       const int g = (int)(2u * y2 + (uint32_t)y);
       if (L.hashed) *reinterpret_cast<uint4*>(r.tab + X.at) = *reinterpret_cast<const uint4*>(X.rowp);
-      X.rowp = L.rows1 + (gl + 8u * (uint32_t)g) * 16u;
+      uint8_t* nrow = L.rows1 + (gl + 8u * (uint32_t)g) * 16u;
+      X.rowp = L.hashed ? nrow : X.rowp;                    // (the other lanes keep scribbling into their own slot)
       X.at = __shfl_sync(ZPQ_FULL, X.nat, (int)gl + 8 * g);
       const uint32_t hz = __shfl_sync(ZPQ_FULL, X.nhz, (int)gl + 8 * g);
       const bool fix = L.hashed && hz != 0u;
@@ -389,8 +412,8 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
           *reinterpret_cast<uint4*>(X.rowp) = v;
           X.at = at;
           const uint32_t bh = (v.x >> 8) & 255u;
-          const uint32_t i0 = L.icm ? bh : bh * 2u;
-          r.cxt = bh; r.t0 = (int)L.map[i0]; r.t1 = (int)L.map[L.isse ? i0 + 1u : i0];
+          const int2 e = *reinterpret_cast<const int2*>(L.mapr + bh * 2u);
+          r.cxt = bh; r.t0 = e.x; r.t1 = e.y;
           const int plead = S.stretch[((uint32_t)r.t0 >> 8) & 32767u];
           const int2 s = fd_slot(L, r.t0, r.t1, plead);
           L.slots[lane] = make_int4(s.x, s.y, s.x, s.y);
@@ -514,6 +537,9 @@ __device__ __forceinline__ void fdec_body(const CodecParams& P, uint8_t* smem) {
   Blk w;
   bind_block(P, smem, w, gw, warp);
   const Plan* plan = P.plan;
+  // small H / M arrays live in the shared slice (the host plans this kernel only then): keep the pointers provably shared
+  if (FD::H_SMEM) w.H = reinterpret_cast<uint32_t*>(smem + P.sm.slices + (uint32_t)warp * P.sm.slice_bytes + plan->smem_h);
+  if (FD::M_SMEM) w.M = smem + P.sm.slices + (uint32_t)warp * P.sm.slice_bytes + plan->smem_m;
   LaneRegs r;
   lane_load(S, P, w, r, gl < FD::N ? gl : 0);
   FdLane L;
@@ -525,9 +551,12 @@ __device__ __forceinline__ void fdec_body(const CodecParams& P, uint8_t* smem) {
     L.cm = owner && ctype == C_CM; L.cons = owner && ctype == C_CONS;
     L.consp = ((int)r.a1 - 128) * 4;
     if (!L.hashedC && ctype != C_CM) { r.tab = w.arena; r.mask = 0; r.a1 = 0; }
-    L.map = L.hashed ? reinterpret_cast<uint32_t*>(w.slice + S.comp[gl].smem_cm)
-                     : reinterpret_cast<uint32_t*>(const_cast<int16_t*>(S.stretch));
     L.rows0 = w.slice + plan->smem_rows; L.rows1 = L.rows0 + 512;
+    L.mapr = L.hashed ? reinterpret_cast<const uint32_t*>(w.slice + S.comp[gl].smem_cm)
+                      : reinterpret_cast<const uint32_t*>(S.stretch);
+    L.mapw = L.hashed ? reinterpret_cast<uint32_t*>(w.slice + S.comp[gl].smem_cm) : reinterpret_cast<uint32_t*>(L.rows0 + lane * 16);
+    L.wmul = L.hashed ? 2u : 0u;
+    for (int k = 0; k < 8; ++k) { int m = lane == k ? -1 : 0; asm volatile("" : "+r"(m)); L.lm[k] = m; }   // opaque: kept in registers, not recomputed
     L.slots = reinterpret_cast<int4*>(w.slice + plan->smem_chain);
     L.cmline = w.slice + plan->smem_fd_cm + (uint32_t)gl * 64u;
     L.mtab = nullptr; L.mbuf = nullptr; L.mmask = L.mmask2 = 0;

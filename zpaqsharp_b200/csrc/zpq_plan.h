@@ -144,12 +144,12 @@ struct BlockResult {
 };
 
 // Read-only tables, built on the host (Predictor.cs:54-67, StateTable.cs) and copied once.
-struct Tables {
+struct Tables {           // the first `SmemLayout::tables_bytes` bytes are staged in shared memory (dt only for models that train a CM / SSE)
   int16_t stretch[32768];
   uint16_t squash[4096];
-  int32_t dt[1024];
   uint16_t dt2k[256];
   uint8_t ns[1024];
+  int32_t dt[1024];
   uint32_t icm_init[256];   // cminit(j)                       Predictor.cs:111-112
   uint32_t isse_init[512];  // {1<<15, clamp512k(stretch(cminit(j)>>8)*1024)}  Predictor.cs:150-155
   uint32_t sse_init[32];    // squash((j&31)*64-992)<<17       Predictor.cs:163-164
@@ -158,6 +158,7 @@ struct Tables {
 // Offsets (bytes) of the CTA-common part of dynamic shared memory.
 struct SmemLayout {
   uint32_t stretch, squash, dt, dt2k, ns, comp, order, steps, mix, hcomp;  // hcomp == kNoSmem: read from the plan
+  uint32_t tables_bytes;  // bytes of Tables staged: 79360 with dt, 75264 without
   uint32_t slices;        // first per-block slice
   uint32_t slice_bytes;   // == plan.smem_warp_bytes
   uint32_t total;         // dynamic shared bytes of the launch
