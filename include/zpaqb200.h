@@ -177,6 +177,8 @@ typedef struct zpq_stats {
   uint64_t state_bytes_per_block;
   char kernel[96];                             /* which coding kernel ran: "lanes/aot2 (HCOMP compiled)", "lanes/nvrtc", ... */
   double post_kernel_ms;                       /* decode: the post-processing pass (PostProcessor.cs:37-86) behind the decoding kernel */
+  uint32_t post_native_blocks;                 /* decode: blocks restored by a native kernel (PASS copy, LZ77, BWT, E8E9) ... */
+  uint32_t post_interpreted_blocks;            /* ... and blocks whose stored PCOMP program was interpreted */
 } zpq_stats;
 int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out);
 
@@ -187,6 +189,13 @@ int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out);
  * NULL) receives the generated text. */
 int64_t zpq_specialize_model(const uint8_t* hdr, uint64_t hdr_len, char* source, uint64_t source_cap, char* log,
                              uint64_t log_cap);
+
+/* Which post-processor the decoder uses for a block whose header says (ph, pm) and whose first segment stores the PCOMP
+ * program pcomp[0..len): 0 = the stored program is interpreted (PostProcessor.write + ZPAQL.run, PostProcessor.cs:37-86);
+ * otherwise kind | e8 << 4 | param << 8 with kind 2 = "lazy2" bit-packed LZ77 (LibZPAQ.cs:430-571; param = rb), 3 = "lzpre"
+ * byte-aligned LZ77 (:577-638; param = minMatch), 4 = "bwtrle" inverse BWT (:644-794), 5 = "e8e9" (:801-826); e8 = the
+ * program ends with the inverse E8E9 pass.  The programs are recognised byte for byte against what makeConfig emits. */
+int64_t zpq_post_kind(int ph, int pm, const uint8_t* pcomp, uint64_t len);
 
 /* Library / build identification: "zpaqb200 <version> sm_100a". */
 const char* zpq_version(void);

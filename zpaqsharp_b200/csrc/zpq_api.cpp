@@ -20,6 +20,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <atomic>
 #include <thread>
 
 #include "zpq_aot.h"
@@ -723,6 +724,8 @@ struct DecBlock {
 
 // ZPQ_FDEC=0 keeps the lane-resident decoders with the post-processor inside (A/B measurements)
 bool want_fast_decode() { const char* e = getenv("ZPQ_FDEC"); return !(e && *e == '0'); }
+// ZPQ_NATIVE_POST=0 sends every block through the PCOMP interpreter pass (test hook: both must restore the same bytes)
+bool want_native_post() { const char* e = getenv("ZPQ_NATIVE_POST"); return !(e && *e == '0'); }
 
 // Blocks [b0, b1) on one device: H2D of their archive bytes, decode (+ post-processing pass), SHA-1, ordered
 // compaction into d.out.  Fills lens / bstat / sha for these blocks; the caller copies d.out to the host.
@@ -753,6 +756,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
   std::vector<uint64_t> slot_off(nbr + 1, 0);
   uint32_t launches = 0;
   double codec_ms = 0, post_ms = 0;
+  uint32_t post_native = 0, post_interp = 0;
   d.t_kern.start(s);
   auto fail_block = [&](uint32_t i, uint8_t st, const std::string& why) {
     bstat[i] = st; R.any_corrupt = true;
@@ -791,33 +795,44 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         std::vector<DecJob> jobs(ids.size());
         std::vector<PostJob> pjobs(ids.size());
         std::vector<DecSeg> segs;
-        Launch L;
-        const uint64_t fr = free_device_memory() + d.arena.cap;
-        const uint64_t reserve = 512ull << 20;
-        plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L, false, false, want_fast_decode());
-        uint64_t raw_total = 0;
+        // every decoder leaves the raw model stream -- PCOMP preamble (<= 64 KB + 3) + transformed data (LZ77 output may
+        // exceed the data by 1/16) -- in d.work; the post-processing pass turns it into the restored bytes in the slots
+        uint64_t raw_total = 0, max_raw = 0;
         for (size_t k = 0; k < ids.size(); ++k) {
           const DecBlock& b = blocks[ids[k]];
           jobs[k].seg_first = (uint32_t)segs.size();
           jobs[k].seg_count = (uint32_t)b.ref.segs.size();
           pjobs[k].out_off = slot_off[ids[k] - b0];
           pjobs[k].out_cap = b.cap;
-          if (L.fast) {
-            // raw model stream: PCOMP preamble (<= 64 KB + 3) + transformed data (LZ77 output may exceed the data by 1/16)
-            jobs[k].out_off = raw_total; jobs[k].out_cap = b.cap + b.cap / 8 + 70000;
-            raw_total = align_up(raw_total + jobs[k].out_cap, 16);
-          } else { jobs[k].out_off = pjobs[k].out_off; jobs[k].out_cap = b.cap; }
+          jobs[k].out_off = raw_total; jobs[k].out_cap = b.cap + b.cap / 8 + 70000;
+          max_raw = std::max(max_raw, jobs[k].out_cap);
+          raw_total = align_up(raw_total + jobs[k].out_cap, 16);
           for (const SegmentRef& sg : b.ref.segs) segs.push_back(DecSeg{b.start - in_base + sg.data_off, sg.data_len});
         }
+        reserve_io(d.work, std::max<uint64_t>(raw_total, 16) + 64, d.arena);       // before the arenas are sized
+        std::vector<PostCandidate> cands;
+        post_candidates(hdr.ph, hdr.pm, cands);
+        std::vector<PostCand> dcands(cands.size());
+        Bytes cand_bytes;
+        bool has_bwt = false;
+        for (size_t k = 0; k < cands.size(); ++k) {
+          dcands[k] = PostCand{cands[k].kind, cands[k].e8, cands[k].param, (uint32_t)cand_bytes.size(), (uint32_t)cands[k].prog.size(), cands[k].wild};
+          cand_bytes.insert(cand_bytes.end(), cands[k].prog.begin(), cands[k].prog.end());
+          has_bwt = has_bwt || cands[k].kind == PK_BWT;
+        }
+        Launch L;
+        const uint64_t fr = free_device_memory() + d.arena.cap;
+        const uint64_t reserve = 512ull << 20;
+        plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L, false, false, want_fast_decode());
         uint64_t mo = 0;
         auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
         const size_t nseg = std::max<size_t>(segs.size(), 1);
         const uint64_t o_jobs = place(sizeof(DecJob) * jobs.size()), o_segs = place(sizeof(DecSeg) * nseg), o_send = place(8ull * nseg),
                        o_pjobs = place(sizeof(PostJob) * jobs.size()), o_raw = place(sizeof(BlockResult) * jobs.size()),
-                       o_res = place(sizeof(BlockResult) * jobs.size()), o_queue = place(512);
+                       o_res = place(sizeof(BlockResult) * jobs.size()), o_queue = place(512), o_kind = place(4ull * jobs.size()),
+                       o_cand = place(sizeof(PostCand) * std::max<size_t>(dcands.size(), 1)), o_cbytes = place(cand_bytes.size() + 16);
         d.meta.reserve(mo);
         uint8_t* meta = d.meta.as<uint8_t>();
-        if (L.fast) reserve_io(d.work, std::max<uint64_t>(raw_total, 16), d.arena);
         d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
         d.plan.reserve(sizeof(Plan));
         CU(cudaMemcpyAsync(d.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
@@ -825,35 +840,47 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         CU(cudaMemcpyAsync(meta + o_jobs, jobs.data(), sizeof(DecJob) * jobs.size(), cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(meta + o_pjobs, pjobs.data(), sizeof(PostJob) * jobs.size(), cudaMemcpyHostToDevice, s));
         if (!segs.empty()) CU(cudaMemcpyAsync(meta + o_segs, segs.data(), sizeof(DecSeg) * segs.size(), cudaMemcpyHostToDevice, s));
+        if (!dcands.empty()) {
+          CU(cudaMemcpyAsync(meta + o_cand, dcands.data(), sizeof(PostCand) * dcands.size(), cudaMemcpyHostToDevice, s));
+          CU(cudaMemcpyAsync(meta + o_cbytes, cand_bytes.data(), cand_bytes.size(), cudaMemcpyHostToDevice, s));
+        }
         CU(cudaMemsetAsync(meta + o_queue, 0, 512, s));
         CodecParams P{};
         P.plan = d.plan.as<Plan>(); P.tab = d.d_tab;
         P.arenas = d.arena.as<uint8_t>(); P.arena_stride = L.plan->arena_bytes;
-        P.in = d.in.as<uint8_t>(); P.out = L.fast ? d.work.as<uint8_t>() : d.slots.as<uint8_t>();
+        P.in = d.in.as<uint8_t>(); P.out = d.work.as<uint8_t>();
         P.djobs = (const DecJob*)(meta + o_jobs); P.segs = (const DecSeg*)(meta + o_segs);
         P.seg_end = (uint64_t*)(meta + o_send);
-        P.results = (BlockResult*)(meta + (L.fast ? o_raw : o_res));
+        P.results = (BlockResult*)(meta + o_raw);
         P.njobs = (uint32_t)jobs.size(); P.resident = L.resident; P.queue = (uint32_t*)(meta + o_queue); P.sm = L.sm;
         d.t_codec.start(s);
         CU(launch_codec(L, P, true, s));
         d.t_codec.stop(s);
         ++launches;
-        if (L.fast) {
+        {
           PostParams Q{};
           Q.plan = d.plan.as<Plan>(); Q.arenas = d.arena.as<uint8_t>(); Q.arena_stride = L.plan->arena_bytes;
           Q.raw = d.work.as<uint8_t>(); Q.djobs = P.djobs; Q.seg_end = P.seg_end; Q.raw_results = (const BlockResult*)(meta + o_raw);
           Q.out = d.slots.as<uint8_t>(); Q.pjobs = (const PostJob*)(meta + o_pjobs); Q.results = (BlockResult*)(meta + o_res);
-          Q.njobs = P.njobs; Q.resident = L.resident; Q.queue = (uint32_t*)(meta + o_queue + 256);
+          Q.njobs = P.njobs; Q.resident = L.resident; Q.queue = (uint32_t*)(meta + o_queue + 256); Q.queue2 = (uint32_t*)(meta + o_queue + 128);
+          Q.jobkind = (uint32_t*)(meta + o_kind);
+          Q.cand_bytes = meta + o_cbytes; Q.cands = (const PostCand*)(meta + o_cand); Q.ncand = (uint32_t)dcands.size();
+          Q.has_bwt = has_bwt ? 1u : 0u; Q.max_raw = max_raw;
           d.t_post.start(s);
+          if (want_native_post()) { CU(launch_post_native(Q, s)); launches += 4; }
+          else CU(cudaMemsetAsync(meta + o_kind, 0, 4ull * jobs.size(), s));
           CU(launch_post(Q, s));
           d.t_post.stop(s);
           ++launches;
         }
         std::vector<BlockResult> r(jobs.size());
+        std::vector<uint32_t> kinds(jobs.size());
         CU(cudaMemcpyAsync(r.data(), meta + o_res, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(kinds.data(), meta + o_kind, 4ull * jobs.size(), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        for (uint32_t kd : kinds) { if ((kd & 15u) == PK_GENERIC) ++post_interp; else ++post_native; }
         codec_ms += d.t_codec.ms();
-        if (L.fast) post_ms += d.t_post.ms();
+        post_ms += d.t_post.ms();
         d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
         snprintf(d.stats.kernel, sizeof d.stats.kernel, "%s", L.kernel.c_str());
         for (size_t k = 0; k < ids.size(); ++k) res[ids[k] - b0] = r[k];
@@ -913,6 +940,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
   }
   d.stats.kernel_ms = d.t_kern.ms(); d.stats.h2d_ms = d.t_h2d.ms();
   d.stats.codec_kernel_ms = codec_ms; d.stats.post_kernel_ms = post_ms; d.stats.launches = launches;
+  d.stats.post_native_blocks = post_native; d.stats.post_interpreted_blocks = post_interp;
 }
 
 void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, uint8_t* out, uint64_t out_cap,
@@ -923,14 +951,16 @@ void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
   std::vector<uint64_t> lens(nb, 0);
   bool any_corrupt = false;
   std::string first_err;
-  for (uint32_t i = 0; i < nb; ++i) {
+  // (finding the end of a segment means looking at every coded byte, Decoder.cs:70-98: the blocks are parsed by all host cores)
+  std::vector<std::string> perr(nb);
+  auto parse_one = [&](uint32_t i) {
     DecBlock& b = blocks[i];
     b.start = in_off[i];
     try {
       parse_block(in + in_off[i], in_off[i + 1] - in_off[i], b.ref);
     } catch (const Failure& f) {
-      bstat[i] = ZPQ_BLOCK_CORRUPT; any_corrupt = true;
-      if (first_err.empty()) first_err = "block " + std::to_string(i) + ": " + f.what();
+      bstat[i] = ZPQ_BLOCK_CORRUPT;
+      perr[i] = "block " + std::to_string(i) + ": " + f.what();
       b.ref.segs.clear();
     }
     uint64_t cap = 0; b.hinted = true;
@@ -942,6 +972,20 @@ void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uin
       else { b.hinted = false; cap += guess; }
     }
     b.cap = cap + 16;
+  };
+  {
+    const uint32_t nt = (uint32_t)std::min<uint64_t>({(uint64_t)std::max(1u, std::thread::hardware_concurrency()), 32ull, (uint64_t)std::max<uint32_t>(nb, 1),
+                                                      std::max<uint64_t>(1, (in_off[nb] - in_off[0]) >> 20)});
+    if (nt <= 1) for (uint32_t i = 0; i < nb; ++i) parse_one(i);
+    else {
+      std::atomic<uint32_t> next{0};
+      std::vector<std::thread> th;
+      for (uint32_t t = 0; t < nt; ++t)
+        th.emplace_back([&]() { for (;;) { const uint32_t i = next.fetch_add(1); if (i >= nb) break; parse_one(i); } });
+      for (auto& t : th) t.join();
+    }
+    for (uint32_t i = 0; i < nb; ++i)
+      if (!perr[i].empty()) { any_corrupt = true; if (first_err.empty()) first_err = perr[i]; }
   }
   // ---- partition over the devices by archive bytes, one host thread per device ----
   const size_t nd = std::min<size_t>(ctx->devs.size(), std::max<uint32_t>(nb, 1));
@@ -1288,6 +1332,20 @@ int64_t zpq_specialize_model(const uint8_t* hdr, uint64_t hdr_len, char* source,
   copy_out(src, source, source_cap);
   copy_out(msg, log, log_cap);
   return size;
+}
+
+int64_t zpq_post_kind(int ph, int pm, const uint8_t* pcomp, uint64_t len) {
+  try {
+    std::vector<PostCandidate> cands;
+    post_candidates(ph, pm, cands);
+    for (const PostCandidate& c : cands) {
+      if (c.prog.size() != len) continue;
+      bool same = true;
+      for (uint64_t i = 0; i < len && same; ++i) same = (int64_t)i == c.wild || pcomp[i] == c.prog[i];
+      if (same) return (int64_t)(c.kind | c.e8 << 4 | (c.wild >= 0 ? (uint32_t)pcomp[c.wild] : c.param) << 8);
+    }
+    return 0;
+  } catch (const Failure& f) { return f.code; }
 }
 
 int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out) {

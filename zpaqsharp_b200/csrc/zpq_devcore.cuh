@@ -740,7 +740,7 @@ __device__ __forceinline__ void encode_lanes_body(const CodecParams& P, uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------
-// Decoder + post-processor body (Decoder.cs:32-158, PostProcessor.cs:37-86)
+// Decoder body (Decoder.cs:32-158); the post-processor (PostProcessor.cs:37-86) is a separate pass over the raw stream
 // ------------------------------------------------------------------------------------------
 template <class Model>
 __device__ __forceinline__ void decode_lanes_body(const CodecParams& P, uint8_t* smem) {
@@ -763,64 +763,10 @@ __device__ __forceinline__ void decode_lanes_body(const CodecParams& P, uint8_t*
     job = __shfl_sync(ZPQ_FULL, job, 0);
     if (job >= P.njobs) break;
     const DecJob J = P.djobs[job];
-    uint8_t* out = P.out + J.out_off;
+    uint8_t* raw = P.out + J.out_off;        // the model's byte stream: PCOMP preamble + transformed data; the post-processor is a separate pass
+    uint64_t rpos = 0;
     lane_begin<Model>(P, S, w, W, r, vm, env, lane);
     uint32_t status = BLK_OK;
-
-    // post-processor (PostProcessor.cs): 0 = expect type, 1 = PASS, 2..4 = loading PROG, 5 = PROG
-    int pstate = 0;
-    uint32_t psize = 0, ploaded = 0;
-    uint8_t* pcode = w.arena + plan->off_pcode;
-    VM pvm; pvm.b = pvm.c = pvm.d = pvm.f = 0;
-    VMEnv penv;
-    penv.code = pcode; penv.len = 0;
-    penv.H = reinterpret_cast<uint32_t*>(w.arena + plan->off_ph); penv.hmask = (1u << plan->ph) - 1;
-    penv.M = w.arena + plan->off_pm; penv.mmask = (uint32_t)((1ull << plan->pm) - 1);
-    penv.R = reinterpret_cast<uint32_t*>(w.arena + plan->off_pr);
-    penv.out = out; penv.out_pos = 0; penv.out_cap = J.out_cap;
-    uint64_t opos = 0, consumed = 0;
-
-    auto post = [&](int c) {
-      switch (pstate) {
-        case 0:
-          if (c < 0 || c > 1) { status = BLK_POSTPROC; return; }
-          pstate = c + 1;
-          break;
-        case 1:
-          if (c >= 0) { if (lane == 0 && opos < J.out_cap) out[opos] = (uint8_t)c; ++opos; }
-          break;
-        case 2:
-          if (c < 0) { status = BLK_POSTPROC; return; }
-          psize = c; pstate = 3;
-          break;
-        case 3:
-          if (c < 0) { status = BLK_POSTPROC; return; }
-          psize += c * 256;
-          if (psize < 1) { status = BLK_POSTPROC; return; }
-          ploaded = 0; pstate = 4;
-          break;
-        case 4:
-          if (c < 0) { status = BLK_POSTPROC; return; }
-          if (lane == 0) pcode[ploaded] = (uint8_t)c;
-          if (++ploaded == psize) {
-            if (lane == 0) { pcode[psize] = 0; pcode[psize + 1] = 0; pcode[psize + 2] = 0; }
-            penv.len = (int)psize;
-            pstate = 5;
-          }
-          break;
-        default: {
-          int rc = 0;
-          __syncwarp();
-          if (lane == 0) {
-            penv.out_pos = opos;
-            rc = zpaql_run(pvm, penv, c < 0 ? 0xFFFFFFFFu : (uint32_t)c, 65536 + 512 * (consumed + J.out_cap));
-          }
-          rc = __shfl_sync(ZPQ_FULL, rc, 0);
-          opos = __shfl_sync(ZPQ_FULL, (unsigned long long)penv.out_pos, 0);
-          if (rc) status = BLK_ZPAQL;
-        }
-      }
-    };
 
     uint32_t low = 1, high = 0xFFFFFFFFu, curr = 0;     // Decoder.init: once per block (Decompresser.cs:128-134), not per segment
     for (uint32_t sg = 0; sg < J.seg_count && status == BLK_OK; ++sg) {
@@ -850,7 +796,6 @@ __device__ __forceinline__ void decode_lanes_body(const CodecParams& P, uint8_t*
         if (status) break;
         if (eos) {
           if (curr != 0) status = BLK_CORRUPT;
-          else post(-1);
           break;
         }
         int c = 1;
@@ -863,14 +808,15 @@ __device__ __forceinline__ void decode_lanes_body(const CodecParams& P, uint8_t*
           status |= lane_advance<Model>(S, W, r, vm, env, lane, y);
         }
         if (status) break;
-        post(c - 256);
-        ++consumed;
+        if (lane == 0 && rpos < J.out_cap) raw[rpos] = (uint8_t)(c - 256);
+        ++rpos;
       }
 #undef ZPQ_DECODE
+      if (lane == 0) P.seg_end[J.seg_first + sg] = rpos;
     }
-    if (status == BLK_OK && opos > J.out_cap) status = BLK_OVERFLOW;
+    if (status == BLK_OK && rpos > J.out_cap) status = BLK_OVERFLOW;
     __syncwarp();
-    if (lane == 0) { P.results[job].out_len = opos; P.results[job].status = status; }
+    if (lane == 0) { P.results[job].out_len = rpos; P.results[job].status = status; }
   }
 }
 

@@ -42,6 +42,9 @@ cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const uin
 
 // Post-processing pass behind the speculative decoder: PostProcessor.write over every job's raw model stream.
 cudaError_t launch_post(const PostParams& q, cudaStream_t s);
+// Native post-processors (zpq_post.cu): classify every job's stored program, run PASS / LZ77 / BWT / E8E9 natively; run before
+// launch_post, which then interprets only what is left (jobkind == PK_GENERIC).
+cudaError_t launch_post_native(const PostParams& q, cudaStream_t s);
 
 // ---- pre-processing (zpq_preproc.cu) ----
 size_t sa_workspace_bytes(uint64_t n_total);

@@ -495,6 +495,46 @@ std::vector<int> take_command(const char*& p) {
 
 }  // namespace
 
+// The PCOMP programs make_config can emit for a block whose header says (ph, pm), assembled: what the decoder's native
+// post-processors (zpq_post.cu) recognise.  LZ77: ph = 0, pm = arg0 + 20 (LibZPAQ.cs:429,576); BWT: ph = pm = arg0 + 20 (:643);
+// E8E9 alone: ph = pm = 0 (:799).  lzpre carries minMatch ("$3") in one operand byte: `wild` is its index.
+void post_candidates(int ph, int pm, std::vector<PostCandidate>& out) {
+  out.clear();
+  auto assemble_post = [](const std::string& text, const int* args) {
+    Bytes hdr, pc;
+    compile_config("comp 0 0 0 0 0 hcomp halt " + text, args, hdr, pc, nullptr);
+    return pc;
+  };
+  int args[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (ph == 0 && pm == 0) {
+    PostCandidate c; c.kind = PK_E8E9; c.e8 = 1; c.param = 0; c.wild = -1; c.prog = assemble_post(kPostE8, args);
+    out.push_back(c);
+  }
+  if (pm >= 20 && pm <= 31) {
+    args[0] = pm - 20;
+    for (int e8 = 0; e8 < 2; ++e8) {
+      if (ph == 0) {
+        PostCandidate c; c.kind = PK_LZ_BITS; c.e8 = e8; c.param = args[0] > 4 ? args[0] - 4 : 0; c.wild = -1;
+        c.prog = assemble_post(post_lz_bits(args, e8 != 0), args);
+        out.push_back(c);
+        PostCandidate d; d.kind = PK_LZ_BYTES; d.e8 = e8; d.param = 0; d.wild = -1;
+        args[2] = 1; d.prog = assemble_post(post_lz_bytes(e8 != 0), args);
+        args[2] = 254; const Bytes other = assemble_post(post_lz_bytes(e8 != 0), args);
+        args[2] = 0;
+        int ndiff = 0;
+        if (other.size() == d.prog.size())
+          for (size_t i = 0; i < other.size(); ++i) if (other[i] != d.prog[i]) { d.wild = (int)i; ++ndiff; }
+        if (ndiff == 1) out.push_back(d);
+      }
+      if (ph == pm) {
+        PostCandidate c; c.kind = PK_BWT; c.e8 = e8; c.param = 0; c.wild = -1;
+        c.prog = assemble_post(post_bwt(args, e8 != 0), args);
+        out.push_back(c);
+      }
+    }
+  }
+}
+
 std::string make_config(const std::string& method, int args[9]) {
   if (method.empty() || !strchr("xs0i", method[0])) throw Failure(ZPQ_E_CONFIG, "method must start with x, s, i or 0");
   const char kind = method[0];

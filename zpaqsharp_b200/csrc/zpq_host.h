@@ -24,6 +24,8 @@ std::string expand_method(const std::string& method, const uint8_t* data, uint64
 std::string make_config(const std::string& method, int args[9]);
 void compile_config(const std::string& text, const int* args, Bytes& hdr, Bytes& pcomp, std::string* pcomp_cmd);
 void builtin_model(int level, Bytes& hdr);
+struct PostCandidate { uint32_t kind, e8, param; int wild; Bytes prog; };
+void post_candidates(int ph, int pm, std::vector<PostCandidate>& out);
 
 // ---- model planning (zpq_model.cpp) ----
 struct Header {           // a parsed block header (ZPAQL.read, ZPAQL.cs:112-156)

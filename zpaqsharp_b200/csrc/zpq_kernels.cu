@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_encode(const CodecParam
 }
 
 // ------------------------------------------------------------------------------------------
-// Decoder kernel: Decoder.cs:32-158 + PostProcessor.cs:37-86 (PCOMP via the ZPAQL interpreter)
+// Decoder kernel: Decoder.cs:32-158; the post-processor (PostProcessor.cs:37-86) is a separate pass over the raw stream
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -355,64 +355,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParam
     job = __shfl_sync(FULL, job, 0);
     if (job >= P.njobs) break;
     const DecJob J = P.djobs[job];
-    uint8_t* out = P.out + J.out_off;
+    uint8_t* raw = P.out + J.out_off;        // the model's byte stream: PCOMP preamble + transformed data; the post-processor is a separate pass
+    uint64_t rpos = 0;
     begin_block(P, S, w, vm, env, lane);
     uint32_t status = ZPQ_BLOCK_OK;
-
-    // post-processor (PostProcessor.cs): 0 = expect type, 1 = PASS, 2..4 = loading PROG, 5 = PROG
-    int pstate = 0;
-    uint32_t psize = 0, ploaded = 0;
-    uint8_t* pcode = w.arena + plan->off_pcode;
-    VM pvm; pvm.b = pvm.c = pvm.d = pvm.f = 0;
-    VMEnv penv;
-    penv.code = pcode; penv.len = 0;
-    penv.H = reinterpret_cast<uint32_t*>(w.arena + plan->off_ph); penv.hmask = (1u << plan->ph) - 1;
-    penv.M = w.arena + plan->off_pm; penv.mmask = (uint32_t)((1ull << plan->pm) - 1);
-    penv.R = reinterpret_cast<uint32_t*>(w.arena + plan->off_pr);
-    penv.out = out; penv.out_pos = 0; penv.out_cap = J.out_cap;
-    uint64_t opos = 0, consumed = 0;
-
-    // Feed one decoded symbol (0..255, or -1 at end of segment) to the post-processor.
-    auto post = [&](int c) {
-      switch (pstate) {
-        case 0:
-          if (c < 0 || c > 1) { status = ZPQ_BLOCK_POSTPROC; return; }
-          pstate = c + 1;
-          break;
-        case 1:
-          if (c >= 0) { if (lane == 0 && opos < J.out_cap) out[opos] = (uint8_t)c; ++opos; }
-          break;
-        case 2:
-          if (c < 0) { status = ZPQ_BLOCK_POSTPROC; return; }
-          psize = c; pstate = 3;
-          break;
-        case 3:
-          if (c < 0) { status = ZPQ_BLOCK_POSTPROC; return; }
-          psize += c * 256;
-          if (psize < 1) { status = ZPQ_BLOCK_POSTPROC; return; }
-          ploaded = 0; pstate = 4;
-          break;
-        case 4:
-          if (c < 0) { status = ZPQ_BLOCK_POSTPROC; return; }
-          if (lane == 0) pcode[ploaded] = (uint8_t)c;
-          if (++ploaded == psize) {
-            if (lane == 0) { pcode[psize] = 0; pcode[psize + 1] = 0; pcode[psize + 2] = 0; }
-            penv.len = (int)psize;
-            pstate = 5;
-          }
-          break;
-        default: {
-          int rc = 0;
-          if (lane == 0) {
-            penv.out_pos = opos;
-            rc = zpaql_run(pvm, penv, c < 0 ? 0xFFFFFFFFu : (uint32_t)c, 65536 + 512 * (consumed + J.out_cap));
-          }
-          rc = __shfl_sync(FULL, rc, 0);
-          opos = __shfl_sync(FULL, (unsigned long long)penv.out_pos, 0);
-          if (rc) status = ZPQ_BLOCK_ZPAQL;
-        }
-      }
-    };
 
     uint32_t low = 1, high = 0xFFFFFFFFu, curr = 0;     // Decoder.init: once per block (Decompresser.cs:128-134), not per segment
     for (uint32_t sg = 0; sg < J.seg_count && status == ZPQ_BLOCK_OK; ++sg) {
@@ -425,14 +371,18 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParam
         return 0;
       };
       if (S.n == 0) {
-        // stored mode (Decoder.cs:56-66)
+        // stored mode (Decoder.cs:56-66): chunks of a 4-byte big-endian length and that many bytes, copied by the 32 lanes
         for (;;) {
           uint32_t len = 0;
           for (int k = 0; k < 4; ++k) len = len << 8 | get();
           if (len == 0 || status) break;
-          for (; len && status == ZPQ_BLOCK_OK; --len) { post((int)get()); ++consumed; }
+          const uint64_t have = seg.in_len - ipos, take = len < have ? len : have;
+          const uint64_t room = rpos < J.out_cap ? J.out_cap - rpos : 0, put = take < room ? take : room;
+          for (uint64_t i = lane; i < put; i += 32) raw[rpos + i] = in[ipos + i];
+          rpos += take; ipos += take;
+          if (take < len) status = ZPQ_BLOCK_CORRUPT;  // "unexpected end of file"
         }
-        if (status == ZPQ_BLOCK_OK) post(-1);
+        if (lane == 0) P.seg_end[J.seg_first + sg] = rpos;
         continue;
       }
       if (curr == 0)                                      // segment initialisation, Decoder.cs:38-42
@@ -454,7 +404,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParam
         if (status) break;
         if (eos) {
           if (curr != 0) status = ZPQ_BLOCK_CORRUPT;  // "decoding end of stream"
-          else post(-1);
           break;
         }
         int c = 1;
@@ -466,14 +415,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) k_zpaq_decode(const CodecParam
           update_bit(S, w, vm, env, lane, y);
         }
         if (w.status) { status = w.status; break; }
-        post(c - 256);
-        ++consumed;
+        if (lane == 0 && rpos < J.out_cap) raw[rpos] = (uint8_t)(c - 256);
+        ++rpos;
       }
 #undef ZPQ_DECODE
+      if (lane == 0) P.seg_end[J.seg_first + sg] = rpos;
     }
-    if (status == ZPQ_BLOCK_OK && opos > J.out_cap) status = ZPQ_BLOCK_OVERFLOW;
+    if (status == ZPQ_BLOCK_OK && rpos > J.out_cap) status = ZPQ_BLOCK_OVERFLOW;
     __syncwarp();
-    if (lane == 0) { P.results[job].out_len = opos; P.results[job].status = status; }
+    if (lane == 0) { P.results[job].out_len = rpos; P.results[job].status = status; }
   }
 }
 
@@ -659,6 +609,7 @@ __global__ void __launch_bounds__(256) k_post(const PostParams Q) {
     if (lane == 0) job = atomicAdd(Q.queue, 1u);
     job = __shfl_sync(FULL, job, 0);
     if (job >= Q.njobs) break;
+    if (Q.jobkind && (Q.jobkind[job] & 15u) != PK_GENERIC) continue;      // restored by a native kernel (zpq_post.cu)
     const DecJob J = Q.djobs[job];
     const PostJob O = Q.pjobs[job];
     const BlockResult R = Q.raw_results[job];

@@ -434,8 +434,18 @@ void parse_block(const uint8_t* p, uint64_t avail, BlockRef& out) {
     seg.data_off = pos;
     if (out.hdr.n > 0) {
       // coded data ends with the first run of >= 4 zero bytes (Decoder.skip)
-      uint32_t last4 = 0xFFFFFFFFu;
-      while (true) { need(1); last4 = last4 << 8 | p[pos++]; if (last4 == 0) break; }
+      // (a run of four zeros contains one of every four consecutive positions: probe every fourth byte)
+      uint64_t k = pos + 3, end4 = 0;
+      while (k < avail) {
+        if (p[k] != 0) { k += 4; continue; }
+        uint64_t lo = k, hi = k;
+        while (lo > pos && p[lo - 1] == 0) --lo;
+        while (hi + 1 < avail && p[hi + 1] == 0) ++hi;
+        if (hi - lo + 1 >= 4) { end4 = lo + 4; break; }
+        k = hi + 4;
+      }
+      if (!end4) throw Failure(ZPQ_E_CORRUPT, "unexpected EOF");
+      pos = end4;
       while (pos < avail && p[pos] == 0) ++pos;
     } else {
       // stored: [len32 BE][bytes]... terminated by a zero length (Decoder.cs:56-66)

@@ -184,6 +184,17 @@ struct CodecParams {
   SmemLayout sm;
 };
 
+// What the post-processing pass does with a job (PostParams::jobkind): kind | e8 << 4 | param << 8.
+// PK_GENERIC = PostProcessor.write with the stored PCOMP program interpreted (any program); the others are native kernels
+// for the PASS type and for the four programs makeConfig emits (LibZPAQ.cs:427-826), recognised by comparing the stored
+// program with the host front end's own output for the block's (ph, pm).
+enum PostKind : uint32_t { PK_GENERIC = 0, PK_PASS = 1, PK_LZ_BITS = 2, PK_LZ_BYTES = 3, PK_BWT = 4, PK_E8E9 = 5 };
+struct PostCand {             // one recognisable program
+  uint32_t kind, e8, param;   // param: LZ_BITS rb (LibZPAQ.cs:427); LZ_BYTES: taken from the program byte at `wild` (minMatch, "$3")
+  uint32_t off, len;          // program bytes at cand_bytes + off
+  int32_t wild;               // index of the one byte that may differ, or -1
+};
+
 struct PostParams {
   const Plan* plan;           // ph, pm and the PCOMP offsets inside an arena
   uint8_t* arenas; uint64_t arena_stride;
@@ -195,7 +206,12 @@ struct PostParams {
   const PostJob* pjobs;
   BlockResult* results;
   uint32_t njobs, resident;
-  uint32_t* queue;
+  uint32_t* queue;            // job counter of the interpreter pass
+  uint32_t* queue2;           // job counter of the native BWT pass
+  uint32_t* jobkind;          // per job, written by the classifier; a native kernel that meets a stream it does not handle puts PK_GENERIC back
+  const uint8_t* cand_bytes; const PostCand* cands; uint32_t ncand;
+  uint32_t has_bwt;           // a PK_BWT candidate exists (the arenas then hold 4 << ph bytes at off_ph for the list)
+  uint64_t max_raw;           // longest raw stream slot (grid sizing of the PASS copy)
 };
 
 struct LaunchGeom {

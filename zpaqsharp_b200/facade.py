@@ -1,13 +1,19 @@
 """The reference's streaming classes on top of the batch C ABI ("streaming facade"): `Compressor`
 (Compressor.cs:12-304), `Decompresser` (Decompresser.cs:13-204), `Reader` (Reader.cs:9-23) and `Writer` (Writer.cs:14-24) with
-the reference's method names, argument meaning, call-order rules and error messages.  A segment is buffered on the host
-and coded by the GPU when it ends (`endSegment` / `endSegmentChecksum`); the bytes reach the Writer in the reference's
-order, so the archive is byte-identical to what the reference's classes write for the same calls.
+the reference's method names, argument meaning, call-order rules and error messages.  A segment is buffered on the host;
+finished blocks are QUEUED and coded by the GPU a wave at a time through one batch call (`batch_blocks` of them are pending,
+`flush()`, `close()` / leaving the `with` block) -- a block coded alone would wait for its own serial bit chain, ~2.5 s per MB
+of mid.cfg, while a wave of 1600 takes the same time.  Everything written after a pending block is held back with it, so the
+bytes reach the Writer in the reference's order and the archive is byte-identical to what the reference's classes write for
+the same calls.  `batch_blocks=1` codes every block when it ends.  The Decompresser decodes a wave of the blocks ahead of the
+one asked for in one call and serves `decompress(n)` from that.
 
 Deliberate limits of the device path, reported through `error()` like any other failure: one segment per block
 (the batch ABI codes independent blocks; SURVEY.md 8f lists multi-segment blocks as a later step).  Nothing here touches
 the oracle: without the CUDA library every call that needs the codec raises."""
 from __future__ import annotations
+
+import hashlib
 
 import numpy as np
 
@@ -81,11 +87,20 @@ class BytesWriter(Writer):
 INIT, BLOCK1, SEG1, BLOCK2, SEG2 = range(5)            # Compressor.cs:314-322
 
 
+class _Pending:
+    """A finished block waiting for the GPU: what goes between its segment header and its end-of-block byte."""
+    __slots__ = ("hdr", "pcomp", "data", "dosha1", "caller_sha1", "keep_sha1", "body")
+
+    def __init__(self, hdr, pcomp, data, dosha1, caller_sha1, keep_sha1):
+        self.hdr, self.pcomp, self.data, self.dosha1 = hdr, pcomp, data, dosha1
+        self.caller_sha1, self.keep_sha1, self.body = caller_sha1, keep_sha1, None
+
+
 class Compressor:
     """Compressor.cs:12-304.  Call order as in the reference: [writeTag] startBlock startSegment [postProcess]
-    compress* endSegment endBlock."""
+    compress* endSegment endBlock.  `flush()` (or `close()`, or leaving a `with` block) codes what is still queued."""
 
-    def __init__(self, ctx: z.Context | None = None):
+    def __init__(self, ctx: z.Context | None = None, batch_blocks: int | None = None):
         self._ctx = ctx
         self._out: Writer | None = None
         self._in: Reader | None = None
@@ -97,6 +112,10 @@ class Compressor:
         self._seg = bytearray()
         self._filename = self._comment = b""
         self._sha1 = b""
+        self._last = b""
+        self._batch = batch_blocks     # None: one resident wave of the model (estimated from its state size)
+        self._queue: list = []         # bytes and _Pending items, in output order, from the first pending block on
+        self._npending = 0
 
     # -- plumbing
     def _c(self) -> z.Context:
@@ -104,7 +123,61 @@ class Compressor:
             self._ctx = z._ctx()
         return self._ctx
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        self.flush()
+
+    def _emit(self, b: bytes):
+        """Bytes for the Writer: at once when no block is pending in front of them."""
+        if self._queue:
+            self._queue.append(bytes(b))
+        else:
+            self._out.write(b)
+
+    def _wave(self, p: _Pending) -> int:
+        if self._batch is not None:
+            return max(1, self._batch)
+        state = z.device_state_bytes(p.hdr)
+        return max(1, min(148 * 16, int(150e9 // (state + 6 * max(len(p.data), 1 << 16)))))
+
+    def flush(self):
+        """Code every queued block (one batch call per model) and hand the held-back bytes to the Writer in order."""
+        if not self._queue:
+            return
+        groups: dict = {}
+        for it in self._queue:
+            if isinstance(it, _Pending):
+                groups.setdefault((it.hdr, it.pcomp, it.dosha1), []).append(it)
+        for (hdr, pcomp, dosha1), items in groups.items():
+            data = b"".join(it.data for it in items)
+            offs = np.concatenate([[0], np.cumsum([len(it.data) for it in items])]).astype(np.uint64)
+            arc, ooff = self._c().compress_blocks_model(data, offs, hdr, pcomp, [0] * 9, None, None, dosha1, False)
+            for i, it in enumerate(items):
+                a = arc[int(ooff[i]):int(ooff[i + 1])].tobytes()
+                # what the library wrote in front of the coded bytes: "zPQ" level 1, header, segment header with its default comment
+                skip = 5 + len(hdr) + 1 + 1 + len(str(len(it.data))) + 1 + 1
+                assert a[:3] == b"zPQ" and a[-1] == 255
+                body = a[skip:-1]
+                if not dosha1:
+                    assert body[-5:] == b"\x00\x00\x00\x00\xfe"
+                    if it.caller_sha1 is not None:
+                        body = body[:-1] + b"\xfd" + bytes(it.caller_sha1[:20])
+                else:
+                    assert body[-25:-20] == b"\x00\x00\x00\x00\xfd"
+                    if not it.keep_sha1:
+                        body = body[:-21] + b"\xfe"
+                it.body = body
+        q, self._queue, self._npending = self._queue, [], 0
+        for it in q:
+            self._out.write(it.body if isinstance(it, _Pending) else it)
+
     def setOutput(self, out: Writer):                  # Compressor.cs:20 (spelled `ssetOutput` there)
+        self.flush()
         self._out = out
 
     ssetOutput = setOutput
@@ -118,7 +191,7 @@ class Compressor:
     # -- block
     def writeTag(self):                                # Compressor.cs:27-43
         assert self._state == INIT
-        self._out.write(TAG)
+        self._emit(TAG)
 
     def startBlock(self, model, args=None, pcomp_cmd: Writer | None = None):
         """startBlock(int level) / startBlock(hcomp bytes) / startBlock(config text, args) -- Compressor.cs:45-116."""
@@ -138,7 +211,7 @@ class Compressor:
         self._hdr = bytes(hdr)
         if len(self._hdr) <= 6:
             error("invalid block header")
-        self._out.write(b"zPQ" + bytes([1 + (self._hdr[6] == 0), 1]) + self._hdr)      # Compressor.cs:91-96
+        self._emit(b"zPQ" + bytes([1 + (self._hdr[6] == 0), 1]) + self._hdr)      # Compressor.cs:91-96
         self._state = BLOCK1
 
     def hcomp(self, out2: Writer):                     # Compressor.cs:123-126
@@ -157,7 +230,7 @@ class Compressor:
             error("the device path codes one segment per block")
         enc = lambda s: b"" if s is None else (s.encode() if isinstance(s, str) else bytes(s))
         self._filename, self._comment = enc(filename), enc(comment)
-        self._out.write(b"\x01" + self._filename + b"\x00" + self._comment + b"\x00\x00")   # Compressor.cs:133-146
+        self._emit(b"\x01" + self._filename + b"\x00" + self._comment + b"\x00\x00")   # Compressor.cs:133-146
         self._seg = bytearray()
         self._pcomp = b""
         self._state = SEG1
@@ -181,7 +254,7 @@ class Compressor:
         if self._state == SEG1:
             self.postProcess()
         assert self._state == SEG2
-        BUFSIZE = 1 << 14
+        BUFSIZE = 1 << 20
         while n:
             nbuf = BUFSIZE if n < 0 or n >= BUFSIZE else n
             buf = self._in.read(nbuf)
@@ -194,55 +267,45 @@ class Compressor:
             self._seg += buf
         return True
 
-    def _flush(self, dosha1: bool) -> bytes:
-        """Code the buffered segment on the GPU; returns the bytes that follow the segment header up to the end of the
-        segment trailer (the end-of-block byte is endBlock's)."""
-        data = bytes(self._seg)
-        arc, _ = self._c().compress_blocks_model(data, np.asarray([0, len(data)], dtype=np.uint64), self._hdr, self._pcomp,
-                                                 [0] * 9, None, None, dosha1, False)
-        a = arc.tobytes()
-        # what the library wrote in front of the coded bytes: "zPQ" level 1, header, segment header with its default comment
-        skip = 5 + len(self._hdr) + 1 + 1 + len(str(len(data))) + 1 + 1
-        assert a[:3] == b"zPQ" and a[-1] == 255
-        return a[skip:-1]
+    def _enqueue(self, dosha1: bool, caller_sha1, keep_sha1: bool):
+        p = _Pending(self._hdr, self._pcomp, bytes(self._seg), dosha1, caller_sha1, keep_sha1)
+        self._last = p.data
+        self._sha1 = b""
+        self._queue.append(p)
+        self._npending += 1
+        self._state = BLOCK2
+        return p
 
     def endSegment(self, sha1string: bytes | None = None):
         """Compressor.cs:224-249: end of data marker, then the caller's SHA-1 (253 + 20 bytes) or 254."""
         if self._state == SEG1:
             self.postProcess()
         assert self._state == SEG2
-        body = self._flush(False)
-        assert body[-5:] == b"\x00\x00\x00\x00\xfe"
-        if sha1string is not None:
-            body = body[:-1] + b"\xfd" + bytes(sha1string[:20])
-        self._out.write(body)
-        self._state = BLOCK2
+        self._enqueue(False, sha1string, False)
 
     def endSegmentChecksum(self, dosha1: bool = True):
-        """Compressor.cs:251-281: as endSegment with the SHA-1 of what was coded (computed on the device).
+        """Compressor.cs:251-281: as endSegment with the SHA-1 of what was coded (the device hashes the block for the trailer).
         Returns (sha1 or None, size) -- the reference returns the hash and writes the size through a pointer."""
         if self._state == SEG1:
             self.postProcess()
         assert self._state == SEG2
-        body = self._flush(True)
-        assert body[-25:-20] == b"\x00\x00\x00\x00\xfd"
-        self._sha1 = body[-20:]
-        if not (self._verify and dosha1):
-            body = body[:-21] + b"\xfe"
-        self._out.write(body)
-        self._state = BLOCK2
-        return (self._sha1 if self._verify else None), len(self._seg)
+        self._enqueue(True, None, bool(self._verify and dosha1))
+        return (self.getChecksum() if self._verify else None), len(self._seg)
 
     def getSize(self) -> int:                          # Compressor.cs:283-286
         return len(self._seg)
 
     def getChecksum(self) -> bytes:                    # Compressor.cs:288-291
+        if not self._sha1:
+            self._sha1 = hashlib.sha1(self._last).digest()
         return self._sha1
 
     def endBlock(self):                                # Compressor.cs:294-299
         assert self._state == BLOCK2
-        self._out.put(255)
+        self._emit(b"\xff")
         self._state = INIT
+        if self._npending and self._npending >= self._wave(next(it for it in self._queue if isinstance(it, _Pending))):
+            self.flush()
 
 
 BLOCK, FILENAME, COMMENT, DATA, SEGEND = range(5)      # Decompresser.cs:206-213
@@ -253,8 +316,10 @@ class Decompresser:
     """Decompresser.cs:13-204.  findBlock reads the archive block from the Reader up to its end-of-block byte; the GPU
     decodes it when decompress() is first called."""
 
-    def __init__(self, ctx: z.Context | None = None):
+    def __init__(self, ctx: z.Context | None = None, batch_blocks: int | None = None):
         self._ctx = ctx
+        self._batch = batch_blocks    # blocks decoded per GPU call (None: up to 2368 blocks / 2 GB of archive ahead)
+        self._cache: dict = {}        # block index -> (restored bytes, sha1 status), decoded ahead
         self._in: Reader | None = None
         self._out: Writer | None = None
         self._state, self._dstate = BLOCK, FIRSTSEG
@@ -276,6 +341,7 @@ class Decompresser:
     def setInput(self, i: Reader):                     # Decompresser.cs:22-25
         self._in = i
         self._arc, self._pos, self._blocks, self._next = b"", 0, [], 0
+        self._cache = {}
 
     def setOutput(self, out: Writer | None):           # Decompresser.cs:113-116
         self._out = out
@@ -369,9 +435,31 @@ class Decompresser:
             error("missing reserved byte")
 
     def _decode(self):
+        """The current block's restored bytes: decoded together with a wave of the blocks behind it (one GPU call)."""
         if self._data is None:
-            out, _, sha, _ = self._c().decompress_blocks(self._blk, np.asarray([0, len(self._blk)], dtype=np.uint64))
-            self._data, self._sha_status = out.tobytes(), int(sha[0])
+            cur = self._next - 1
+            if cur not in self._cache:
+                self._cache = {}
+                limit = self._batch if self._batch is not None else 148 * 16
+                hi, nbytes = cur, 0
+                while hi < len(self._blocks) and hi - cur < max(1, limit) and nbytes < (2 << 30):
+                    nbytes += self._blocks[hi][1] - self._blocks[hi][0]
+                    hi += 1
+                a = np.frombuffer(self._arc, dtype=np.uint8)
+                pieces = [a[s:e] for s, e in self._blocks[cur:hi]]
+                cat = np.concatenate(pieces) if len(pieces) > 1 else pieces[0]
+                offs = np.concatenate([[0], np.cumsum([p.size for p in pieces])]).astype(np.uint64)
+                try:
+                    out, ooff, sha, _ = self._c().decompress_blocks(cat, offs)
+                except z.ZpaqError:
+                    if hi - cur == 1:
+                        raise
+                    # a damaged block somewhere ahead must not fail this one: decode it alone
+                    out, ooff, sha, _ = self._c().decompress_blocks(pieces[0], offs[:2])
+                    hi = cur + 1
+                for k in range(hi - cur):
+                    self._cache[cur + k] = (out[int(ooff[k]):int(ooff[k + 1])].tobytes(), int(sha[k]))
+            self._data, self._sha_status = self._cache.pop(cur)
             self._dstate = SEG
 
     def decompress(self, n: int = -1) -> bool:

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "zpq_make_config", "zpq_expand_method", "zpq_compile_config", "zpq_builtin_model", "zpq_block_memory",
     "zpq_device_state_bytes", "zpq_compress_blocks", "zpq_compress_blocks_level", "zpq_compress_blocks_model",
     "zpq_compress_blocks_model_dev", "zpq_find_blocks", "zpq_decompress_blocks", "zpq_decompressed_bound",
-    "zpq_get_stats", "zpq_version", "zpq_specialize_model", "zpq_encoder_plan",
+    "zpq_get_stats", "zpq_version", "zpq_specialize_model", "zpq_encoder_plan", "zpq_post_kind",
 ]
 
 
@@ -43,7 +43,8 @@ class Stats(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
                 ("codec_kernel_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches", C.c_uint32), ("resident_blocks", C.c_uint32), ("state_bytes_per_block", C.c_uint64),
-                ("kernel", C.c_char * 96), ("post_kernel_ms", C.c_double)]
+                ("kernel", C.c_char * 96), ("post_kernel_ms", C.c_double),
+                ("post_native_blocks", C.c_uint32), ("post_interpreted_blocks", C.c_uint32)]
 
 
 _lib = None
@@ -179,6 +180,14 @@ def encoder_plan(hdr: bytes, smem_bytes: int = 232448, blocks_per_sm: int = 32) 
         raise ZpaqError(rc, "zpq_encoder_plan failed")
     keys = ["applies", "lanes_per_block", "roles", "blocks_per_sm", "smem_per_block", "coder_delay", "mixer_role", "warps_per_cta"]
     return dict(zip(keys, [int(v) for v in out]))
+
+
+def post_kind(ph: int, pm: int, pcomp: bytes) -> int:
+    """How the decoder restores a block with this PCOMP program: 0 = interpreted, else kind | e8 << 4 | param << 8 (see the header)."""
+    L = load()
+    L.zpq_post_kind.restype = C.c_int64
+    L.zpq_post_kind.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint64]
+    return int(L.zpq_post_kind(ph, pm, bytes(pcomp), len(pcomp)))
 
 
 def specialize_model(hdr: bytes):
