@@ -20,13 +20,24 @@ class StandInContext:
     """Answers compress_blocks_model / decompress_blocks like zpaqsharp_b200.libzpaq.Context, computed by the oracle."""
 
     def compress_blocks_model(self, data, offsets, hdr, pcomp=b"", args=None, filename=None, comment=None, dosha1=True, with_tag=True, out=None):
-        assert len(offsets) == 2
-        a = po.compress_with_model(bytes(hdr), bytes(pcomp), [0] * 9, bytes(data), filename, comment if comment else str(len(data)), dosha1, with_tag)
-        return np.frombuffer(a, dtype=np.uint8), np.asarray([0, len(a)], dtype=np.uint64)
+        self.calls = getattr(self, "calls", 0) + 1
+        data = bytes(data)
+        arcs = []
+        for i in range(len(offsets) - 1):
+            b = data[int(offsets[i]):int(offsets[i + 1])]
+            arcs.append(po.compress_with_model(bytes(hdr), bytes(pcomp), [0] * 9, b, filename if i == 0 else None,
+                                               comment if (comment and i == 0) else str(len(b)), dosha1, with_tag))
+        return np.frombuffer(b"".join(arcs), dtype=np.uint8), np.concatenate([[0], np.cumsum([len(a) for a in arcs])]).astype(np.uint64)
 
     def decompress_blocks(self, archive, offsets, out=None):
-        got, st = po.decompress(TAGGED(bytes(archive)))
-        return np.frombuffer(got, dtype=np.uint8), np.asarray([0, len(got)], dtype=np.uint64), np.asarray([st[0] if st else 0], dtype=np.uint8), np.zeros(1, np.uint8)
+        self.dcalls = getattr(self, "dcalls", 0) + 1
+        archive = bytes(archive)
+        outs, shas = [], []
+        for i in range(len(offsets) - 1):
+            got, st = po.decompress(TAGGED(archive[int(offsets[i]):int(offsets[i + 1])]))
+            outs.append(got); shas.append(st[0] if st else 0)
+        return (np.frombuffer(b"".join(outs), dtype=np.uint8), np.concatenate([[0], np.cumsum([len(o) for o in outs])]).astype(np.uint64),
+                np.asarray(shas, dtype=np.uint8), np.zeros(len(outs), np.uint8))
 
 
 def TAGGED(blk: bytes) -> bytes:
@@ -153,3 +164,74 @@ def test_decompresser_facade_errors():
     d.setInput(F.BytesReader(bytes(bad)))
     with pytest.raises(z.ZpaqError, match="unsupported ZPAQ level"):
         d.findBlock()
+
+
+def test_compressor_queues_blocks_and_codes_them_in_one_call():
+    """Finished blocks wait for a wave (Compressor.cs:193-248 on a device that only pays off in batches): nothing a later block
+    writes may overtake them, one batch call codes them all, and the archive is what block-at-a-time coding gives."""
+    ctx = StandInContext()
+    w = F.BytesWriter()
+    parts = [synth.blocks("mixed", 80 + i, 1, 3000 + 500 * i).tobytes() for i in range(5)]
+    with F.Compressor(ctx, batch_blocks=4) as co:
+        co.setOutput(w)
+        for i, part in enumerate(parts):
+            co.writeTag()
+            co.startBlock(1 if i != 3 else 2)                      # block 3 uses another model: its own batch call
+            co.startSegment("f%d" % i, None)
+            co.setInput(F.BytesReader(part))
+            co.compress()
+            if i % 2:
+                co.endSegment(hashlib.sha1(part).digest())
+            else:
+                co.setVerify(True)
+                sha, size = co.endSegmentChecksum()
+                assert sha == hashlib.sha1(part).digest() and size == len(part)
+            co.endBlock()
+            if i == 0:
+                held = len(w.buf)                                    # tag, block header and segment header of block 0 went straight through
+            if i < 3:
+                assert len(w.buf) == held and getattr(ctx, "calls", 0) == 0   # everything behind them is still queued
+            if i == 3:
+                # the fourth pending block starts the wave: two models -> two batch calls (hdr/pcomp/checksum mode group the blocks)
+                assert ctx.calls >= 2 and len(w.buf) > 0
+    want = b"".join(po.compress_block_level(p, 1 if i != 3 else 2, filename="f%d" % i, comment="") for i, p in enumerate(parts))
+    assert w.getvalue() == want
+
+
+def test_reading_the_writer_flushes_and_batch_one_is_immediate():
+    part = synth.blocks("text", 90, 1, 5000).tobytes()
+    for batch in (None, 1):
+        ctx = StandInContext()
+        w = F.BytesWriter()
+        co = F.Compressor(ctx, batch_blocks=batch)
+        co.setOutput(w)
+        co.startBlock(1)
+        co.startSegment(None, None)
+        co.setInput(F.BytesReader(part))
+        co.compress()
+        co.endSegment()
+        co.endBlock()
+        if batch == 1:
+            assert len(w.buf) > 100                                  # coded when the block ended
+        got = w.getvalue()                                           # reading the Writer codes what is queued
+        assert got == po.compress_block_level(part, 1, comment="", dosha1=False, with_tag=False)
+
+
+def test_decompresser_decodes_a_wave_ahead():
+    parts = [synth.blocks("mixed", 95 + i, 1, 2000 + 100 * i).tobytes() for i in range(6)]
+    arc = b"".join(po.compress_block_level(p, 1) for p in parts)
+    ctx = StandInContext()
+    d = F.Decompresser(ctx, batch_blocks=4)
+    d.setInput(F.BytesReader(arc))
+    got = []
+    while d.findBlock():
+        while d.findFilename():
+            d.readComment()
+            out = F.BytesWriter()
+            d.setOutput(out)
+            d.decompress()
+            d.readSegmentEnd()
+            assert d.sha1_verified() == 1
+            got.append(out.getvalue())
+    assert got == parts
+    assert ctx.dcalls == 2                                           # 6 blocks in waves of 4

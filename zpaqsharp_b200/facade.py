@@ -71,8 +71,11 @@ class BytesReader(Reader):
 
 
 class BytesWriter(Writer):
+    """Collects the bytes; reading them (`getvalue`) first makes the Compressors writing here code what they still hold."""
+
     def __init__(self):
         self.buf = bytearray()
+        self._producers: list = []
 
     def put(self, c: int):
         self.buf.append(c & 255)
@@ -81,6 +84,8 @@ class BytesWriter(Writer):
         self.buf += buf
 
     def getvalue(self) -> bytes:
+        for p in list(self._producers):
+            p.flush()
         return bytes(self.buf)
 
 
@@ -179,6 +184,9 @@ class Compressor:
     def setOutput(self, out: Writer):                  # Compressor.cs:20 (spelled `ssetOutput` there)
         self.flush()
         self._out = out
+        prod = getattr(out, "_producers", None)
+        if isinstance(prod, list) and self not in prod:
+            prod.append(self)                          # a Writer that can be read back asks for the queued blocks first
 
     ssetOutput = setOutput
 
