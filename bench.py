@@ -349,7 +349,7 @@ def run_reference(args):
 def wave_blocks(cfg_id: str, n_gpus_unused: int = 1) -> int:
     """Blocks of one resident wave on a 180 GB B200 (what bench.py codes per GPU and step; deterministic so that the reference
     arm, which has no GPU to ask, names the same config)."""
-    return {"C2a": 1607}.get(cfg_id, CONFIGS[cfg_id]["max_blocks"])
+    return {"C2a": 1628, "C4": 592}.get(cfg_id, CONFIGS[cfg_id]["max_blocks"])
 
 
 def workload_config(cfg_id, batch_blocks, n_gpus):
@@ -414,7 +414,7 @@ def measure_config(rig: Rig, cfg_id: str, steps: int, warmup: int, batch_blocks:
     bs = cfg["block"]
     how, arg = cfg["how"]
     hdr, pcomp, margs = model_of(cfg)
-    state = z.device_state_bytes(hdr)
+    state = z.device_state_bytes(hdr, False, bs)
     free, _ = torch.cuda.mem_get_info()
     if batch_blocks:
         B = batch_blocks
@@ -422,6 +422,12 @@ def measure_config(rig: Rig, cfg_id: str, steps: int, warmup: int, batch_blocks:
         io_per_block = bs * 6                         # input + slots + out + pre-processing work, device resident path
         B = int((free - (3 << 30)) // (state + io_per_block))
         B = max(1, min(B, cfg["max_blocks"]))
+        try:                                          # one wave of the role-split encoder, when it applies
+            ep = z.encoder_plan(hdr)
+            if ep["applies"]:
+                B = min(B, ep["blocks_per_sm"] * torch.cuda.get_device_properties(rig.local).multi_processor_count)
+        except Exception:
+            pass
     first = (rig.rank * B) % TOTAL_BLOCKS             # weak scaling: every GPU codes a full wave of its own blocks
 
     host_in = torch.empty(B * bs, dtype=torch.uint8).pin_memory()

@@ -93,6 +93,10 @@ double zpq_block_memory(const uint8_t* hdr, uint64_t hdr_len);
 /* Bytes of device state one resident block of this model needs (tables + H/M/R), i.e. what the
  * scheduler divides free HBM by.  Negative on error. */
 int64_t zpq_device_state_bytes(const uint8_t* hdr, uint64_t hdr_len, int for_decode);
+/* The same when no block of the batch is longer than max_block_bytes: a MATCH component's history buffer (Predictor.cs:114-119,
+ * ht of 2^bufbits bytes indexed by the stream position) is then allocated at the size the stream can reach, which holds the same
+ * bytes at every index the component forms (mid.cfg with 1 MB blocks: 97 MB instead of 111 MB per block). */
+int64_t zpq_device_state_bytes_for(const uint8_t* hdr, uint64_t hdr_len, int for_decode, uint64_t max_block_bytes);
 
 /* How the role-split encoder (zpq_duo.cuh) would run this model with `smem_bytes` of shared memory per SM and
  * `blocks_per_sm` resident blocks wanted: the device analogue of asking the reference whether its x86 JIT applies

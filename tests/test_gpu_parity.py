@@ -310,3 +310,27 @@ def test_role_split_encoder_many_blocks_per_sm(gpu_ctx, oracle):
         assert a[int(ooff[i]):int(ooff[i + 1])] == oracle.compress_block_level(data[i * size:(i + 1) * size], 2), i
     out, _, sha, bst = gpu_ctx.decompress_blocks(arc, ooff)
     assert out.tobytes() == data and set(sha.tolist()) == {1}
+
+
+def test_level5_analysis_on_the_device_matches_oracle(gpu_ctx, oracle, zlib_):
+    # LibZPAQ.cs:242-280: levels 5..9 pick periodic models from the byte-gap histogram of each block; the histogram is
+    # counted on the device (k_gap_hist), the resulting method -- and so the archive -- must be the oracle's
+    from oracle import frontend as fe
+    from tools import synth
+    rng = np.random.default_rng(3)
+    rec37 = (bytes(range(37)) * 3000)[:90000]                                       # period 37
+    rec300 = bytes(rng.integers(0, 256, 300, dtype=np.uint8)) * 250                # period 300 (> 255: no second model)
+    mixed = synth.blocks("mixed", 650, 1, 70000).tobytes()
+    tiny = b"abcabcabc"
+    parts = [rec37, mixed, rec300, tiny, b"", rec37[:5000] + mixed[:5000]]
+    data = b"".join(parts)
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.uint64)
+    for method in ("5", "58,200,1"):
+        want_methods = [fe.expand_method(method, p) for p in parts]
+        assert "c0,0,1036,255i1" in want_methods[0] and "c0,0,1299,255i1" in want_methods[2]
+        assert [zlib_.expand_method(method, p) for p in parts] == want_methods
+        arc, ooff = gpu_ctx.compress_blocks(data, offs, method)
+        ref = b"".join(oracle.compress_block(p, method) for p in parts)
+        assert arc.tobytes() == ref
+        out, _, sha, _ = gpu_ctx.decompress_blocks(arc, ooff)
+        assert out.tobytes() == data and set(sha.tolist()) == {1}

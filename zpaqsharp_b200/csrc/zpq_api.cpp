@@ -179,9 +179,9 @@ uint32_t common_smem(const Plan& pl, SmemLayout& L) {
 bool force_generic();
 
 void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint64_t mem_for_arenas, uint32_t max_resident,
-                 Launch& L, bool want_skew = false, bool want_duo = false, bool want_fast = false) {
+                 Launch& L, bool want_skew = false, bool want_duo = false, bool want_fast = false, uint64_t max_stream = 0) {
   L.plan.reset(new Plan);
-  build_plan(hdr, decode, 48 * 1024, *L.plan);
+  build_plan(hdr, decode, 48 * 1024, *L.plan, 0, false, max_stream);
   L.skewed = false; L.duo = false; L.wb = 0; L.fast = false;
   uint64_t fit = mem_for_arenas / std::max<uint64_t>(L.plan->arena_bytes, 1);
   if (fit < 1) throw Failure(ZPQ_E_NOMEM, "model state does not fit in device memory");
@@ -200,7 +200,7 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
     const uint32_t G = (uint32_t)spec.duo_g, B = 32 / G;
     {
       std::unique_ptr<Plan> probe(new Plan);
-      build_plan(hdr, false, 48 * 1024, *probe, (int)G);
+      build_plan(hdr, false, 48 * 1024, *probe, (int)G, false, max_stream);
       L.duo_roles = probe->duo_split ? 4 : 3;
     }
     const uint32_t max_groups = 15u / L.duo_roles;     // 16 warps per CTA, one of them the arithmetic coder
@@ -211,7 +211,7 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
     for (uint32_t w = wb; w >= 1 && !L.duo; --w) {
       const uint32_t common = common_smem(*L.plan, L.sm);
       const uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
-      build_plan(hdr, false, (avail / w) & ~127u, *L.plan, (int)G);
+      build_plan(hdr, false, (avail / w) & ~127u, *L.plan, (int)G, false, max_stream);
       if (L.plan->duo_ok && L.plan->pipe_maps && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.duo = true; wb = w; }
     }
     if (L.duo) {
@@ -228,14 +228,14 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
       L.resident = (uint32_t)res;
       return;
     }
-    build_plan(hdr, decode, 48 * 1024, *L.plan);
+    build_plan(hdr, decode, 48 * 1024, *L.plan, 0, false, max_stream);
   }
   if (want_fast && has_spec && spec.dec_fast && decode) {
     // Speculative decoder (zpq_fdec.cuh): one warp per block, every ICM/ISSE map in the block's shared slice
     for (uint32_t w = std::min(W, 12u); w >= 1 && !L.fast; --w) {      // kFdecThreads = 384
       const uint32_t common = common_smem(*L.plan, L.sm);
       const uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
-      build_plan(hdr, true, (avail / w) & ~127u, *L.plan, 0, true);
+      build_plan(hdr, true, (avail / w) & ~127u, *L.plan, 0, true, max_stream);
       const bool hm_ok = ((4ull << hdr.hh) > 2048 || L.plan->smem_h != kNoSmem) && ((1ull << hdr.hm) > 1024 || L.plan->smem_m != kNoSmem);
       if (L.plan->pipe_maps && hm_ok && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.fast = true; W = w; }
     }
@@ -252,7 +252,7 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
       L.resident = (uint32_t)resident;
       return;
     }
-    build_plan(hdr, decode, 48 * 1024, *L.plan);
+    build_plan(hdr, decode, 48 * 1024, *L.plan, 0, false, max_stream);
   }
   if (want_skew && has_spec && !decode) {
     // The time-skewed encoder (zpq_pipe.cuh) keeps every ICM/ISSE map in the block's shared slice:
@@ -260,10 +260,10 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
     for (uint32_t w = W; w >= 1 && !L.skewed; --w) {
       const uint32_t common = common_smem(*L.plan, L.sm);
       const uint32_t avail = d.smem_optin > common ? d.smem_optin - common : 0;
-      build_plan(hdr, decode, (avail / w) & ~127u, *L.plan);
+      build_plan(hdr, decode, (avail / w) & ~127u, *L.plan, 0, false, max_stream);
       if (L.plan->pipe_ok && L.plan->pipe_maps && (uint64_t)w * L.plan->smem_warp_bytes <= avail) { L.skewed = true; W = w; }
     }
-    if (!L.skewed) build_plan(hdr, decode, 48 * 1024, *L.plan);
+    if (!L.skewed) build_plan(hdr, decode, 48 * 1024, *L.plan, 0, false, max_stream);
   }
   for (;;) {
     uint32_t common = common_smem(*L.plan, L.sm);
@@ -272,7 +272,7 @@ void plan_launch(Device& d, const Header& hdr, bool decode, uint64_t want, uint6
     uint32_t budget = avail / W;
     uint32_t minimal = (uint32_t)align_up(24ull * std::max(hdr.n, 1) + 64 + 1024 + 256, 128) + (hdr.n <= 32 ? 4096u : 0u);
     if (budget >= minimal) {
-      build_plan(hdr, decode, budget & ~127u, *L.plan);
+      build_plan(hdr, decode, budget & ~127u, *L.plan, 0, false, max_stream);
       common = common_smem(*L.plan, L.sm);
       avail = d.smem_optin > common ? d.smem_optin - common : 0;
       if ((uint64_t)W * L.plan->smem_warp_bytes <= avail) break;
@@ -444,7 +444,8 @@ uint64_t compress_on_device(zpq_ctx* ctx, Device& d, CompressTask& T, uint8_t* h
     const bool fits = max_block + max_block / 16 + preamble.size() + 64 < (1ull << 28);
     const bool want_skew = !(e && *e == '0') && fits;
     const bool want_duo = !(e2 && *e2 == '0') && fits;
-    plan_launch(d, M.hdr, false, nb, fr > reserve ? fr - reserve : 0, ctx->max_resident, L, want_skew, want_duo);
+    plan_launch(d, M.hdr, false, nb, fr > reserve ? fr - reserve : 0, ctx->max_resident, L, want_skew, want_duo, false,
+                max_block + max_block / 16 + preamble.size() + 64);
     d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
   } else {
     plan_launch(d, M.hdr, false, nb, 1ull << 30, ctx->max_resident, L);
@@ -702,6 +703,37 @@ void compress_model(zpq_ctx* ctx, const Model& M, const uint8_t* in, const uint6
   for (size_t k = 0; k < nd; ++k) if (codes[k]) throw Failure(codes[k], errs[k]);
 }
 
+// The data analysis of method levels 5..9 (LibZPAQ.cs:242-258) for every block of a batch, on device 0: byte-gap histograms,
+// kGapBins ints per block.  The blocks go up in pieces of about 1 GB; the models are then derived on the host from 16 KB per block.
+void device_gap_histograms(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, std::vector<int>& gaps) {
+  Device& d = ctx->devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t s = d.stream;
+  gaps.assign((size_t)nb * kGapBins, 0);
+  uint32_t b0 = 0;
+  while (b0 < nb) {
+    uint32_t b1 = b0 + 1;
+    while (b1 < nb && in_off[b1 + 1] - in_off[b0] <= (1ull << 30)) ++b1;
+    const uint32_t cnt = b1 - b0;
+    const uint64_t bytes = in_off[b1] - in_off[b0];
+    uint64_t max_len = 0;
+    for (uint32_t b = b0; b < b1; ++b) max_len = std::max(max_len, in_off[b + 1] - in_off[b]);
+    reserve_io(d.in, bytes + 64, d.arena);
+    uint64_t mo = 0;
+    auto place = [&](uint64_t n) { uint64_t o = mo; mo = align_up(mo + n, 256); return o; };
+    const uint64_t o_off = place(8ull * (cnt + 1)), o_gap = place(4ull * cnt * kGapBins);
+    d.meta.reserve(mo);
+    uint8_t* meta = d.meta.as<uint8_t>();
+    if (bytes) CU(cudaMemcpyAsync(d.in.p, in + in_off[b0], bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(meta + o_off, in_off + b0, 8ull * (cnt + 1), cudaMemcpyHostToDevice, s));
+    CU(launch_gap_hist(d.in.as<uint8_t>(), (const uint64_t*)(meta + o_off), cnt, max_len, (int*)(meta + o_gap), s));
+    CU(cudaMemcpyAsync(gaps.data() + (size_t)b0 * kGapBins, meta + o_gap, 4ull * cnt * kGapBins, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    b0 = b1;
+  }
+}
+
+
 void model_from_header_bytes(const uint8_t* hdr, uint64_t hdr_len, const uint8_t* pcomp, uint64_t pcomp_len, const int* args9,
                              Model& M) {
   if (!hdr || hdr_len < 8) throw Failure(ZPQ_E_ARG, "missing block header");
@@ -823,7 +855,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         Launch L;
         const uint64_t fr = free_device_memory() + d.arena.cap;
         const uint64_t reserve = 512ull << 20;
-        plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L, false, false, want_fast_decode());
+        plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L, false, false, want_fast_decode(), max_raw);
         uint64_t mo = 0;
         auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
         const size_t nseg = std::max<size_t>(segs.size(), 1);
@@ -1176,6 +1208,19 @@ int64_t zpq_device_state_bytes(const uint8_t* hdr, uint64_t hdr_len, int for_dec
   return rc ? rc : v;
 }
 
+int64_t zpq_device_state_bytes_for(const uint8_t* hdr, uint64_t hdr_len, int for_decode, uint64_t max_block_bytes) {
+  int64_t v = -1;
+  int rc = guarded(nullptr, [&]() {
+    Header h; parse_header(hdr, hdr_len, h);
+    std::unique_ptr<Plan> p(new Plan);
+    // the stream bound the schedulers use: compress_on_device (transformed block + preamble), decompress_range (raw slot)
+    const uint64_t bound = for_decode ? max_block_bytes + 16 + (max_block_bytes + 16) / 8 + 70000 : max_block_bytes + max_block_bytes / 16 + 65536 + 3 + 64;
+    build_plan(h, for_decode != 0, 48 * 1024, *p, 0, false, max_block_bytes ? bound : 0);
+    v = (int64_t)p->arena_bytes;
+  });
+  return rc ? rc : v;
+}
+
 int zpq_encoder_plan(const uint8_t* hdr, uint64_t hdr_len, uint32_t smem_bytes, uint32_t blocks_per_sm, int32_t* out8) {
   if (!hdr || !out8) return ZPQ_E_ARG;
   return guarded(nullptr, [&]() {
@@ -1238,10 +1283,14 @@ int zpq_compress_blocks(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off,
     // form one device batch
     uint32_t i = 0;
     uint64_t base = 0;
+    // levels 5..9 choose their periodic models from the block's byte-gap histogram (LibZPAQ.cs:242-280): counted on the device
+    std::vector<int> gaps;
+    const bool analyse = method_needs_analysis(method);
+    if (analyse) device_gap_histograms(ctx, in, in_off, nb, gaps);
     while (i < nb) {
       auto derive = [&](uint32_t b, Model& M) {
         const uint64_t n = in_off[b + 1] - in_off[b];
-        std::string x = expand_method(method, in + in_off[b], n);
+        std::string x = expand_method_gaps(method, n, analyse ? gaps.data() + (size_t)b * kGapBins : nullptr);
         std::string cfg = make_config(x, M.args);
         Bytes h;
         compile_config(cfg, M.args, h, M.pcomp, nullptr);

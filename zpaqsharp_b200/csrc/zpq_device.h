@@ -70,5 +70,7 @@ struct LzParams {            // LZBuffer constructor arguments, LZBuffer.cs:151-
   uint32_t minMatch, minMatch2, maxMatch, maxLiteral, lookahead, bucket, shift1, shift2, minMatchBoth, rb;
 };
 cudaError_t launch_lz77(const LzParams& p, cudaStream_t s);
+// Byte-gap histograms (4096 bins per block) for the data analysis of method levels 5..9 (LibZPAQ.cs:242-258).
+cudaError_t launch_gap_hist(const uint8_t* in, const uint64_t* d_off, uint32_t nb, uint64_t max_len, int* gap, cudaStream_t s);
 
 }  // namespace zpq

@@ -297,7 +297,28 @@ int block_arg0(uint64_t n) {  // LibZPAQ.cs:125
   return v > 0 ? v : 0;
 }
 
+// Byte-gap histogram of a block (LibZPAQ.cs:242-258): gap[k] = positions whose byte last occurred k positions earlier, the
+// "last occurrence" of a byte not seen yet being position 0.  Host form; k_gap_hist (zpq_preproc.cu) is the device form.
+void gap_histogram(const uint8_t* data, uint64_t n, int* gap) {
+  for (int k = 0; k < kGapBins; ++k) gap[k] = 0;
+  int last[256] = {0};
+  for (uint64_t i = 0; i < n; ++i) {
+    const int k = (int)i - last[data[i]];
+    if (k > 0 && k < kGapBins) ++gap[k];
+    last[data[i]] = (int)i;
+  }
+}
+
+bool method_needs_analysis(const std::string& method) { return !method.empty() && method[0] >= '5' && method[0] <= '9'; }
+
 std::string expand_method(const std::string& method, const uint8_t* data, uint64_t n) {
+  if (!method_needs_analysis(method)) return expand_method_gaps(method, n, nullptr);
+  std::vector<int> gap(kGapBins, 0);
+  gap_histogram(data, n, gap.data());
+  return expand_method_gaps(method, n, gap.data());
+}
+
+std::string expand_method_gaps(const std::string& method, uint64_t n, const int* gaps) {
   if (method.empty()) throw Failure(ZPQ_E_ARG, "empty method");
   if (!isdigit((unsigned char)method[0])) return method;
   const int arg0 = block_arg0(n);
@@ -352,16 +373,9 @@ std::string expand_method(const std::string& method, const uint8_t* data, uint64
   m += "," + num(doe8);
   m += (type & 1) ? "w2c0,1010,255i1" : "w1i1";
   m += "c256ci1,1,1,1,1,1,2a";
-  const int NR = 1 << 12;
-  std::vector<int> gap(NR, 0);
-  {
-    int last[256] = {0};
-    for (uint64_t i = 0; i < n; ++i) {
-      const int k = (int)i - last[data[i]];
-      if (k > 0 && k < NR) ++gap[k];
-      last[data[i]] = (int)i;
-    }
-  }
+  const int NR = kGapBins;
+  if (!gaps) throw Failure(ZPQ_E_ARG, "method levels 5..9 need the block's byte-gap histogram");
+  std::vector<int> gap(gaps, gaps + NR);
   int rest = (int)n - gap[1] - gap[2] - gap[3];
   for (int pass = 0; pass < 2; ++pass) {
     int period = 0, seen = 0;

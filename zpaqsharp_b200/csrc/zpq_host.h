@@ -21,6 +21,10 @@ struct Failure : std::runtime_error {
 int comp_len(int type);
 int block_arg0(uint64_t n);
 std::string expand_method(const std::string& method, const uint8_t* data, uint64_t n);
+constexpr int kGapBins = 1 << 12;        // NR, LibZPAQ.cs:242
+bool method_needs_analysis(const std::string& method);      // levels 5..9 look at the data (LibZPAQ.cs:242-280)
+void gap_histogram(const uint8_t* data, uint64_t n, int* gap /*kGapBins*/);
+std::string expand_method_gaps(const std::string& method, uint64_t n, const int* gaps /*kGapBins, or null for levels 0..4*/);
 std::string make_config(const std::string& method, int args[9]);
 void compile_config(const std::string& text, const int* args, Bytes& hdr, Bytes& pcomp, std::string* pcomp_cmd);
 void builtin_model(int level, Bytes& hdr);
@@ -40,7 +44,8 @@ double header_memory(const Header& h);  // ZPAQL.memory(), ZPAQL.cs:58-81
 // Build the device plan.  smem_budget = shared bytes one resident block may use for its slice.
 // duo_g != 0 lays the shared slice out for the two-role encoder (zpq_duo.cuh) with duo_g lanes per block.
 // fdec lays it out for the speculative decoder (zpq_fdec.cuh).
-void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& plan, int duo_g = 0, bool fdec = false);
+// max_stream != 0: no stream coded with this plan is longer (lets a MATCH buffer be allocated at the size the streams can reach).
+void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& plan, int duo_g = 0, bool fdec = false, uint64_t max_stream = 0);
 void build_tables(Tables& t);           // throws if the squash/stretch checksums are off
 void sha1_host(const uint8_t* p, uint64_t n, uint8_t out[20]);
 

@@ -134,7 +134,7 @@ void build_tables(Tables& t) {
 }
 
 // ------------------------------------------------------------------------------------------
-void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl, int duo_g, bool fdec) {
+void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl, int duo_g, bool fdec, uint64_t max_stream) {
   memset(&pl, 0, sizeof(Plan) - sizeof(pl.hcomp));
   pl.n = h.n; pl.hh = h.hh; pl.hm = h.hm; pl.ph = h.ph; pl.pm = h.pm;
   if (h.hh > 28 || h.hm > 30 || h.ph > 28 || h.pm > 30)
@@ -293,9 +293,21 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
       case C_MATCH:
         if (bits > 32 || cp[2] > 32) throw Failure(ZPQ_E_CONFIG, "max size for MATCH is 32 32");
         if (bits > 29 || cp[2] > 31) throw Failure(ZPQ_E_UNSUPPORTED, "MATCH larger than the device build supports");
-        d.mask = (1u << bits) - 1; d.mask2 = (uint32_t)((1ull << cp[2]) - 1);
-        d.tab = take(4ull << bits); fill(d.tab, 4ull << bits, 0, 0, false);
-        d.tab2 = take(1ull << cp[2]); fill(d.tab2, 1ull << cp[2], 0, 0, false);
+        {
+          // The buffer is indexed by the stream position (Predictor.cs:382-411: limit counts bytes and wraps at 2^cp[2]) and by
+          // positions up to 256 + limit bytes in front of it, which wrap to the unwritten, zeroed top of the buffer.  When no
+          // stream of the launch reaches 2^k - 1024 bytes, a 2^k-byte buffer therefore holds the same bytes at every index the
+          // component can form: it is allocated (and cleared) at that size instead of 2^cp[2] (mid.cfg: 2 MB instead of 16 MB).
+          int bb = cp[2];
+          if (max_stream) {
+            int need = 12;
+            while ((1ull << need) < max_stream + 1024) ++need;
+            bb = std::min(bb, need);
+          }
+          d.mask = (1u << bits) - 1; d.mask2 = (uint32_t)((1ull << bb) - 1);
+          d.tab = take(4ull << bits); fill(d.tab, 4ull << bits, 0, 0, false);
+          d.tab2 = take(1ull << bb); fill(d.tab2, 1ull << bb, 0, 0, false);
+        }
         break;
       case C_AVG:
         if (cp[1] >= i) throw Failure(ZPQ_E_CONFIG, "AVG j >= i");

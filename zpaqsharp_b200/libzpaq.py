@@ -25,7 +25,7 @@ E_ARG, E_CONFIG, E_CUDA, E_NOMEM, E_OUTPUT, E_CORRUPT, E_UNSUPPORTED = -1, -2, -
 ABI_SYMBOLS = [
     "zpq_create", "zpq_destroy", "zpq_last_error", "zpq_set_stream", "zpq_set_max_resident",
     "zpq_make_config", "zpq_expand_method", "zpq_compile_config", "zpq_builtin_model", "zpq_block_memory",
-    "zpq_device_state_bytes", "zpq_compress_blocks", "zpq_compress_blocks_level", "zpq_compress_blocks_model",
+    "zpq_device_state_bytes", "zpq_device_state_bytes_for", "zpq_compress_blocks", "zpq_compress_blocks_level", "zpq_compress_blocks_model",
     "zpq_compress_blocks_model_dev", "zpq_find_blocks", "zpq_decompress_blocks", "zpq_decompressed_bound",
     "zpq_get_stats", "zpq_version", "zpq_specialize_model", "zpq_encoder_plan", "zpq_post_kind",
 ]
@@ -165,8 +165,14 @@ def block_memory(hdr: bytes) -> float:
     return load().zpq_block_memory(hdr, len(hdr))
 
 
-def device_state_bytes(hdr: bytes, for_decode: bool = False) -> int:
-    return load().zpq_device_state_bytes(hdr, len(hdr), 1 if for_decode else 0)
+def device_state_bytes(hdr: bytes, for_decode: bool = False, max_block_bytes: int = 0) -> int:
+    """Device state of one resident block; with max_block_bytes, as the scheduler sizes it for a batch of such blocks."""
+    L = load()
+    if max_block_bytes:
+        L.zpq_device_state_bytes_for.restype = C.c_int64
+        L.zpq_device_state_bytes_for.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64]
+        return L.zpq_device_state_bytes_for(hdr, len(hdr), 1 if for_decode else 0, max_block_bytes)
+    return L.zpq_device_state_bytes(hdr, len(hdr), 1 if for_decode else 0)
 
 
 def encoder_plan(hdr: bytes, smem_bytes: int = 232448, blocks_per_sm: int = 32) -> dict:
