@@ -62,7 +62,7 @@ CONFIGS = {
             "kind": "mixed", "block": BLOCK, "how": ("method", lzcm_method(0)), "max_blocks": 592,
             "metric": "compress MB/s, LZ77+ICM/ISSE+MIX 1 MB blocks, byte-exact"},
     "C3": {"what": "configs[2]: method 32,128,1 = x2,3ci1 (BWT + ICM/ISSE), 4,190,208-byte blocks of synthetic text",
-           "kind": "text", "block": BLOCK_4MB, "how": ("method", bwt_method(2)), "max_blocks": 148,
+           "kind": "text", "block": BLOCK_4MB, "how": ("method", bwt_method(2)), "max_blocks": 592,
            "metric": "compress MB/s, method 3 (BWT) 4 MB blocks, byte-exact"},
     "C4": {"what": "configs[3]: max.cfg (Compressor.startBlock(3), 22 components: CONST/ICM/ISSE chain/MATCH/MIX/MIX2/SSE with a word-model HCOMP), 1 MB mixed blocks",
            "kind": "mixed", "block": BLOCK, "how": ("level", 3), "max_blocks": 740,
@@ -349,7 +349,7 @@ def run_reference(args):
 def wave_blocks(cfg_id: str, n_gpus_unused: int = 1) -> int:
     """Blocks of one resident wave on a 180 GB B200 (what bench.py codes per GPU and step; deterministic so that the reference
     arm, which has no GPU to ask, names the same config)."""
-    return {"C2a": 1628, "C4": 592}.get(cfg_id, CONFIGS[cfg_id]["max_blocks"])
+    return {"C2a": 1776, "C4": 740}.get(cfg_id, CONFIGS[cfg_id]["max_blocks"])
 
 
 def workload_config(cfg_id, batch_blocks, n_gpus):
@@ -404,7 +404,7 @@ class Rig:
 
 
 def measure_config(rig: Rig, cfg_id: str, steps: int, warmup: int, batch_blocks: int = 0, sample_clocks: bool = False,
-                   timed_decompress_reps: int = 1):
+                   timed_decompress_reps: int = 1, warm_host_path: bool = True):
     """One config on this rank's GPU: device-resident compress (CUDA events), e2e compress and e2e decompress through the
     host-buffer ABI (pinned buffers, copies inside the timed region), round trip checked."""
     import torch
@@ -478,7 +478,8 @@ def measure_config(rig: Rig, cfg_id: str, steps: int, warmup: int, batch_blocks:
     torch.cuda.empty_cache()
 
     # ---- timed: end to end through the host-buffer ABI ----
-    archive, hoff = step_host()            # warm the host path (pinned buffers, staging)
+    if warm_host_path:
+        archive, hoff = step_host()        # warm the host path (pinned buffers, staging)
     rig.barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
@@ -545,7 +546,7 @@ def summarise(r, world):
             "compression_ratio": r["ratio"], "state_bytes_per_block": r["state"], "n_gpus": world}
 
 
-def c5_sweep(rig: Rig):
+def c5_sweep(rig: Rig, full: bool = False):
     """BASELINE configs[4] / SURVEY 8d C5: mixed-method archives (equal quarters of mid.cfg, bit-packed LZ77 stored, byte LZ77 + CM
     chain, BWT blocks, interleaved) at four block payloads, decompressed through the host-buffer ABI.  The archives are written by
     this library (byte-identical to the oracle's, tests/test_gpu_parity.py)."""
@@ -553,7 +554,10 @@ def c5_sweep(rig: Rig):
     from tools import synth
     z, ctx = rig.z, rig.ctx
     rows = []
-    for bs, per_method in ((262144, 128), (BLOCK, 48), (BLOCK_4MB, 12), (BLOCK_16MB, 3)):
+    # about 1 GB of blocks per payload size; a block is restored at the speed of its own serial bit chain whatever the batch, so
+    # the 16 MB leg takes minutes (a 16 MB mid.cfg block: ~40 s to code, ~90 s to decode) and runs only with --config C5
+    legs = ((262144, 1024), (BLOCK, 256), (BLOCK_4MB, 64)) + (((BLOCK_16MB, 16),) if full else ())
+    for bs, per_method in legs:
         a0 = 0 if bs <= BLOCK else (2 if bs == BLOCK_4MB else 4)
         groups = [("level", 2, "mixed"), ("method", lz_method(a0), "mixed"), ("method", lzcm_method(a0), "mixed"), ("method", bwt_method(a0), "text")]
         arcs, datas = [], []
@@ -694,15 +698,18 @@ def main():
             if cid == head_id:
                 continue
             try:
-                rc = measure_config(rig, cid, 1, 1)
+                rig.close(); rig.open()                 # the library's buffers are grow-only: every config starts from an empty device
+                rc = measure_config(rig, cid, 1, 1, warm_host_path=False)
                 line["gpu_launches"] += rc["launches"]
                 configs[cid] = summarise(rc, world)
                 del rc
             except Exception as e:                      # a config that fails is reported, it does not take the headline down
                 configs[cid] = {"error": str(e)[:300]}
         try:
+            rig.close(); rig.open()
             configs["C5"] = {"workload": "configs[4]: mixed-method archive decompression sweep (mid.cfg / LZ77 stored / LZ77+CM / BWT blocks interleaved)",
-                             "sweep": c5_sweep(rig)}
+                             "sweep": c5_sweep(rig, full=args.config == "C5"),
+                             "note": None if args.config == "C5" else "the 16,773,120-byte leg runs with --config C5 (profiles/ holds the last full sweep)"}
         except Exception as e:
             configs["C5"] = {"error": str(e)[:300]}
     lib_multi = None

@@ -39,6 +39,8 @@ namespace ZPAQSharp
         [DllImport(Lib)] public static extern long zpq_builtin_model(int level, byte* hdr, ulong hdrCap);
         [DllImport(Lib)] public static extern double zpq_block_memory(byte* hdr, ulong hdrLen);
         [DllImport(Lib)] public static extern long zpq_device_state_bytes(byte* hdr, ulong hdrLen, int forDecode);
+        [DllImport(Lib)] public static extern long zpq_device_state_bytes_for(byte* hdr, ulong hdrLen, int forDecode, ulong maxBlockBytes);
+        [DllImport(Lib)] public static extern long zpq_post_kind(int ph, int pm, byte* pcomp, ulong len);
         [DllImport(Lib)] public static extern int zpq_encoder_plan(byte* hdr, ulong hdrLen, uint smemBytes, uint blocksPerSm, int* out8);
     }
 
@@ -128,15 +130,24 @@ namespace ZPAQSharp
         }
     }
     /// <summary>Replacement body of Compressor (Compressor.cs:12-304) over the batch ABI: same methods, same call order,
-    /// same bytes.  A segment is buffered and coded by the GPU in endSegment; one segment per block.  The Python model of
-    /// this class, zpaqsharp_b200/facade.py, is what the tests run (tests/test_facade_host.py, tests/test_gpu_facade.py).</summary>
-    public unsafe class CompressorB200
+    /// same bytes.  A segment is buffered; finished blocks are QUEUED and coded by the GPU a wave at a time through one
+    /// zpq_compress_blocks_model call per model (when BatchBlocks of them are pending, on flush() and on Dispose()): a block
+    /// coded alone waits for its own serial bit chain, a wave of 1600 takes the same time.  Everything written after a
+    /// pending block is held back with it, so the Writer receives the reference's bytes in the reference's order.
+    /// One segment per block.  The Python model of this class, zpaqsharp_b200/facade.py, is what the tests run
+    /// (tests/test_facade_host.py, tests/test_gpu_facade.py).</summary>
+    public unsafe class CompressorB200 : IDisposable
     {
         enum State { INIT, BLOCK1, SEG1, BLOCK2, SEG2 }
+        sealed class Pending { public byte[] hdr, pcomp, data, sha1; public byte[] body; }
         State state = State.INIT;
         Writer output; Reader input;
         byte[] hdr = new byte[0], pz = new byte[0], pcomp = new byte[0];
         readonly System.IO.MemoryStream seg = new System.IO.MemoryStream();
+        readonly System.Collections.Generic.List<object> queue = new System.Collections.Generic.List<object>();   // byte[] | Pending, in output order
+        int npending;
+        /// <summary>Blocks that wait for one GPU call (1 = code every block when it ends).</summary>
+        public int BatchBlocks = 1600;
         static IntPtr ctx;
         static IntPtr Ctx()
         {
@@ -145,12 +156,68 @@ namespace ZPAQSharp
             return ctx;
         }
 
-        public void setOutput(Writer o) { output = o; }
+        void emit(params byte[] b)
+        {
+            if (queue.Count > 0) queue.Add(b);
+            else foreach (byte x in b) output.put(x);
+        }
+        static bool same(byte[] a, byte[] b) { return a.Length == b.Length && System.Linq.Enumerable.SequenceEqual(a, b); }
+
+        /// <summary>Code every queued block (one batch call per model) and hand the held-back bytes to the Writer in order.</summary>
+        public void flush()
+        {
+            var todo = new System.Collections.Generic.List<Pending>();
+            foreach (object it in queue) if (it is Pending p) todo.Add(p);
+            while (todo.Count > 0)
+            {
+                Pending first = todo[0];
+                var group = todo.FindAll(q => same(q.hdr, first.hdr) && same(q.pcomp, first.pcomp));
+                todo.RemoveAll(q => group.Contains(q));
+                ulong total = 0;
+                var off = new ulong[group.Count + 1];
+                for (int i = 0; i < group.Count; ++i) { off[i] = total; total += (ulong)group[i].data.Length; }
+                off[group.Count] = total;
+                var data = new byte[total + 1];
+                for (int i = 0; i < group.Count; ++i) Array.Copy(group[i].data, 0, data, (long)off[i], group[i].data.Length);
+                var outBuf = new byte[(long)total + (long)total / 4 + (first.hdr.Length + first.pcomp.Length * 4 + 65536L) * group.Count];
+                var outOff = new ulong[group.Count + 1];
+                var args = new int[9];
+                fixed (byte* ph = first.hdr, pp = first.pcomp, pi = data, po = outBuf)
+                fixed (ulong* poff = off, pooff = outOff)
+                fixed (int* pa = args)
+                {
+                    int rc = ZpaqB200Native.zpq_compress_blocks_model(Ctx(), ph, (ulong)first.hdr.Length, first.pcomp.Length > 0 ? pp : null,
+                                                                      (ulong)first.pcomp.Length, pa, pi, poff, (uint)group.Count, null, null, 0, 0,
+                                                                      po, (ulong)outBuf.Length, pooff);
+                    if (rc != 0) LibZPAQ.error(Marshal.PtrToStringAnsi(ZpaqB200Native.zpq_last_error(ctx)));
+                }
+                for (int i = 0; i < group.Count; ++i)
+                {
+                    // the library wrote "zPQ" level 1, the header and a segment header with its default comment (the decimal size)
+                    // in front of the coded bytes, and 254 255 behind them; this class has written its own headers already
+                    int n = group[i].data.Length;
+                    long skip = (long)outOff[i] + 5 + first.hdr.Length + 1 + 1 + n.ToString().Length + 1 + 1;
+                    long end = (long)outOff[i + 1] - 2;          // up to and including the four zero bytes
+                    var body = new System.IO.MemoryStream();
+                    body.Write(outBuf, (int)skip, (int)(end - skip));
+                    if (group[i].sha1 != null) { body.WriteByte(253); body.Write(group[i].sha1, 0, 20); }
+                    else body.WriteByte(254);
+                    group[i].body = body.ToArray();
+                }
+            }
+            var q2 = queue.ToArray();
+            queue.Clear(); npending = 0;
+            foreach (object it in q2)
+                foreach (byte x in (it is Pending p2 ? p2.body : (byte[])it)) output.put(x);
+        }
+        public void Dispose() { flush(); }
+
+        public void setOutput(Writer o) { if (output != null) flush(); output = o; }
         public void setInput(Reader i) { input = i; }
 
         public void writeTag()                                   // Compressor.cs:27-43
         {
-            foreach (byte b in new byte[] { 0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3 }) output.put(b);
+            emit(0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3);
         }
 
         public void startBlock(int level)                        // Compressor.cs:45-83
@@ -167,22 +234,19 @@ namespace ZPAQSharp
         public void startBlock(byte[] hcomp)                     // Compressor.cs:85-99
         {
             hdr = hcomp; pz = new byte[0];
-            output.put('z'); output.put('P'); output.put('Q');
-            output.put(1 + (hdr[6] == 0 ? 1 : 0));
-            output.put(1);
-            foreach (byte b in hdr) output.put(b);
+            emit((byte)'z', (byte)'P', (byte)'Q', (byte)(1 + (hdr[6] == 0 ? 1 : 0)), 1);
+            emit(hdr);
             state = State.BLOCK1;
         }
 
         public void startSegment(string filename = null, string comment = null)   // Compressor.cs:133-146
         {
             if (state == State.BLOCK2) LibZPAQ.error("the device path codes one segment per block");
-            output.put(1);
-            if (filename != null) foreach (char c in filename) output.put(c);
-            output.put(0);
-            if (comment != null) foreach (char c in comment) output.put(c);
-            output.put(0);
-            output.put(0);
+            emit(1);
+            if (filename != null) emit(System.Text.Encoding.Latin1.GetBytes(filename));
+            emit(0);
+            if (comment != null) emit(System.Text.Encoding.Latin1.GetBytes(comment));
+            emit(0, 0);
             seg.SetLength(0);
             pcomp = new byte[0];
             state = State.SEG1;
@@ -218,38 +282,16 @@ namespace ZPAQSharp
         public void endSegment(byte[] sha1string = null)         // Compressor.cs:224-249
         {
             if (state == State.SEG1) postProcess();
-            byte[] data = seg.ToArray();
-            var off = new ulong[] { 0, (ulong)data.Length };
-            var outBuf = new byte[data.Length + data.Length / 4 + hdr.Length + pcomp.Length * 4 + 65536];
-            var outOff = new ulong[2];
-            var args = new int[9];
-            fixed (byte* ph = hdr, pp = pcomp, pi = data, po = outBuf)
-            fixed (ulong* poff = off, pooff = outOff)
-            fixed (int* pa = args)
-            {
-                int rc = ZpaqB200Native.zpq_compress_blocks_model(Ctx(), ph, (ulong)hdr.Length, pcomp.Length > 0 ? pp : null, (ulong)pcomp.Length, pa,
-                                                                  pi, poff, 1, null, null, 0, 0, po, (ulong)outBuf.Length, pooff);
-                if (rc != 0) LibZPAQ.error(Marshal.PtrToStringAnsi(ZpaqB200Native.zpq_last_error(ctx)));
-            }
-            // the library wrote "zPQ" level 1, the header and a segment header with its default comment (the decimal size)
-            // in front of the coded bytes, and 254 255 behind them; this class has written its own headers already
-            int skip = 5 + hdr.Length + 1 + 1 + data.Length.ToString().Length + 1 + 1;
-            int end = (int)outOff[1] - 2;                        // up to and including the four zero bytes
-            for (int i = skip; i < end; ++i) output.put(outBuf[i]);
-            if (sha1string != null)
-            {
-                output.put(253);
-                for (int i = 0; i < 20; ++i) output.put(sha1string[i]);
-            }
-            else
-                output.put(254);
+            queue.Add(new Pending { hdr = hdr, pcomp = pcomp, data = seg.ToArray(), sha1 = sha1string });
+            ++npending;
             state = State.BLOCK2;
         }
 
         public void endBlock()                                   // Compressor.cs:294-299
         {
-            output.put(255);
+            emit(255);
             state = State.INIT;
+            if (npending >= BatchBlocks) flush();
         }
     }
 }
