@@ -462,6 +462,19 @@ __global__ void k_sha1(const uint8_t* data, const uint64_t* off, const uint32_t*
   uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
   uint32_t w[16];
   uint64_t pos = 0;
+  if (((uintptr_t)p & 15u) == 0) {
+    // block starts and slots are 16-byte aligned: a 64-byte chunk is four 16-byte loads, byte order swapped by PRMT
+    for (; pos + 64 <= n; pos += 64) {
+      const uint4* q = reinterpret_cast<const uint4*>(p + pos);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 v = q[k];
+        w[4 * k] = __byte_perm(v.x, 0, 0x0123); w[4 * k + 1] = __byte_perm(v.y, 0, 0x0123);
+        w[4 * k + 2] = __byte_perm(v.z, 0, 0x0123); w[4 * k + 3] = __byte_perm(v.w, 0, 0x0123);
+      }
+      sha1_chunk(h, w);
+    }
+  }
   for (; pos + 64 <= n; pos += 64) {
 #pragma unroll
     for (int k = 0; k < 16; ++k)
@@ -490,7 +503,9 @@ __global__ void k_sha1(const uint8_t* data, const uint64_t* off, const uint32_t*
 cudaError_t launch_sha1(const uint8_t* data, const uint64_t* off, const uint32_t* len, uint32_t nb, uint8_t* digests,
                         cudaStream_t s) {
   if (!nb) return cudaSuccess;
-  k_sha1<<<(nb + 31) / 32, 32, 0, s>>>(data, off, len, nb, digests);
+  // one thread per block is the unit (SHA-1 is a serial chain); 8 threads per CTA spread them over the SMs so that each
+  // thread's loads do not queue behind 31 others on one load-store unit
+  k_sha1<<<(nb + 7) / 8, 8, 0, s>>>(data, off, len, nb, digests);
   return cudaGetLastError();
 }
 
