@@ -38,3 +38,29 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "MB/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_names_the_same_config_as_the_gpu_arm():
+    """`same_config` of the driver compares the two arms' `config`: every key must be filled in on the CPU arm too."""
+    import bench
+    for cid in ("C2a", "C1", "C4"):
+        cfg = bench.workload_config(cid, None, 1)
+        assert cfg["batch_blocks_per_gpu"] and cfg["block_bytes"] == bench.CONFIGS[cid]["block"] and cfg["config_id"] == cid
+        assert all(v is not None for v in cfg.values())
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--config", "C1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert d["impl"] == "reference" and d["config"]["config_id"] == "C1" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+
+
+def test_algorithmic_bytes_of_the_survey():
+    """A(C2a) = 950 B per input byte, A(C1) = 66."""
+    import bench
+    from zpaqsharp_b200 import libzpaq as z
+    hdr = z.builtin_model(2)
+    a = bench.algorithmic_bytes(hdr, 111424512, bench.BLOCK, 0.3, 0)
+    assert abs(a - 950) < 1.0
+    text, args = z.make_config("x0,0c256,0,255,255")
+    h1, _ = z.compile_config(text, args)
+    assert abs(bench.algorithmic_bytes(h1, 1 << 20, bench.BLOCK, 0.3, 0) - 66.3) < 0.5
