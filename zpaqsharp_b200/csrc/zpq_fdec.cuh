@@ -164,9 +164,11 @@ struct FdLane {
   bool icm, isse, hashed, cm, cons;   // what this lane OWNS (lanes 0..7 only)
   bool hashedC;                       // component (lane & 7) is hashed (helper lanes mirror it)
   int consp;                          // CONS: its prediction (Predictor.cs:96-98)
-  const uint32_t* mapr;               // ICM / ISSE map in the shared slice, 8-byte entries ({p, -} / {weight, bias}); a readable dummy elsewhere
+  const uint32_t* mapr;               // ICM / ISSE map in the shared slice: 4-byte entries {p} (ICM) / 8-byte entries {weight, bias} (ISSE); a readable dummy elsewhere
   uint32_t* mapw;                     // the same for stores; lanes without a map write their own scratch words
-  uint32_t wmul;                      // 2 (words per entry) or 0
+  uint32_t rmul;                      // words per entry when reading: 1 (ICM) or 2
+  uint32_t wmul;                      // ... when storing: 1, 2, or 0 for lanes without a map
+  uint32_t ymul;                      // word offset of the second value of an entry: 1 (ISSE, scratch) or 0 (ICM: there is none)
   uint8_t* rows0; uint8_t* rows1;     // the block's row buffers: 32 x 16 bytes each
   int4* slots;                        // 32 x {x0, y0, x1, y1}
   uint8_t* cmline;                    // CM: this lane's 16-entry line in shared memory
@@ -174,6 +176,12 @@ struct FdLane {
   // MATCH tables (warp-uniform)
   uint32_t* mtab; uint8_t* mbuf; uint32_t mmask, mmask2;
 };
+
+// map entry of bit history bh: {p, p} for an ICM, {weight, bias} for an ISSE
+__device__ __forceinline__ int2 fd_map_read(const FdLane& L, uint32_t bh) {
+  const uint32_t* q = L.mapr + bh * L.rmul;
+  return make_int2((int)q[0], (int)q[L.ymul]);
+}
 
 // slot of this lane for one outcome: what the other lanes need to evaluate the component
 __device__ __forceinline__ int2 fd_slot(const FdLane& L, int x, int y, int plead) {
@@ -212,7 +220,7 @@ __device__ __forceinline__ void fd_begin_byte(const Shared& S, FdCtx<FD>& X, con
   int plead = L.cons ? L.consp : 0;
   if (FD::M_ICM | FD::M_ISSE) {
     const uint32_t bh = (v.x >> 8) & 255u;
-    const int2 e = *reinterpret_cast<const int2*>(L.mapr + bh * 2u);
+    const int2 e = fd_map_read(L, bh);
     if (FD::M_CM == 0 || L.hashed) { r.cxt = bh; r.t0 = e.x; r.t1 = e.y; }
     if (L.icm) plead = S.stretch[((uint32_t)r.t0 >> 8) & 32767u];
   }
@@ -259,8 +267,8 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
         const uint8_t* base = L.rows1 + (gl + 16u * y2) * 16u;
         nb0 = base[1]; nb1 = base[8 * 16 + 1];
       }
-      e0 = *reinterpret_cast<const int2*>(L.mapr + nb0 * 2u);
-      e1 = *reinterpret_cast<const int2*>(L.mapr + nb1 * 2u);
+      e0 = fd_map_read(L, nb0);
+      e1 = fd_map_read(L, nb1);
     }
     if (FD::M_CM) {
       if (!NIB_END) {
@@ -352,7 +360,11 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
   // ---- F: commit this bit, become bit K+1 ----
   if (FD::M_ICM | FD::M_ISSE) {
     // lanes without a map store into their own scratch (entry 0 of their row slot)
-    *reinterpret_cast<int2*>(L.mapw + (r.cxt & 255u) * L.wmul) = make_int2(y ? t1x : t0x, y ? t1y : t0y);
+    {
+      uint32_t* q = L.mapw + (r.cxt & 255u) * L.wmul;
+      q[L.ymul] = (uint32_t)(y ? t1y : t0y);          // (an ICM entry has one word: the next store overwrites this one)
+      q[0] = (uint32_t)(y ? t1x : t0x);
+    }
     X.rowp[(uint32_t)X.hmap4 & 15u] = (uint8_t)(y ? nx1 : nx0);
   }
   if (FD::M_CM) {
@@ -412,7 +424,7 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
           *reinterpret_cast<uint4*>(X.rowp) = v;
           X.at = at;
           const uint32_t bh = (v.x >> 8) & 255u;
-          const int2 e = *reinterpret_cast<const int2*>(L.mapr + bh * 2u);
+          const int2 e = fd_map_read(L, bh);
           r.cxt = bh; r.t0 = e.x; r.t1 = e.y;
           const int plead = S.stretch[((uint32_t)r.t0 >> 8) & 32767u];
           const int2 s = fd_slot(L, r.t0, r.t1, plead);
@@ -555,7 +567,9 @@ __device__ __forceinline__ void fdec_body(const CodecParams& P, uint8_t* smem) {
     L.mapr = L.hashed ? reinterpret_cast<const uint32_t*>(w.slice + S.comp[gl].smem_cm)
                       : reinterpret_cast<const uint32_t*>(S.stretch);
     L.mapw = L.hashed ? reinterpret_cast<uint32_t*>(w.slice + S.comp[gl].smem_cm) : reinterpret_cast<uint32_t*>(L.rows0 + lane * 16);
-    L.wmul = L.hashed ? 2u : 0u;
+    L.rmul = L.icm ? 1u : 2u;
+    L.wmul = L.icm ? 1u : L.isse ? 2u : 0u;
+    L.ymul = L.icm ? 0u : 1u;
     for (int k = 0; k < 8; ++k) { int m = lane == k ? -1 : 0; asm volatile("" : "+r"(m)); L.lm[k] = m; }   // opaque: kept in registers, not recomputed
     L.slots = reinterpret_cast<int4*>(w.slice + plan->smem_chain);
     L.cmline = w.slice + plan->smem_fd_cm + (uint32_t)gl * 64u;

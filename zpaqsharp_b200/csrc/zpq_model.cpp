@@ -284,7 +284,7 @@ void build_plan(const Header& h, bool for_decode, uint32_t smem_budget, Plan& pl
         if (bits > 26) throw Failure(ZPQ_E_CONFIG, "max size for ICM is 26");
         d.mask = (uint32_t)((64ull << bits) - 16);
         d.tab = take(64ull << bits); fill(d.tab, 64ull << bits, 0, 0, false, 3);
-        if (duo_g) {   // the coder role owns ICM maps and addresses them with a 4-byte stride
+        if (duo_g || fdec) {   // the coder role (zpq_duo.cuh) / the speculative decoder (zpq_fdec.cuh) address ICM maps with a 4-byte stride
           if (slice + 1024 <= smem_budget) { d.smem_cm = stake(1024); fill(d.smem_cm, 1024, 4, 0, true, 1); }
           else { d.tab2 = take(1024); fill(d.tab2, 1024, 4, 0, false, 1); }
         } else if (slice + 2048 <= smem_budget) { d.smem_cm = stake(2048); fill(d.smem_cm, 2048, 1, 0, true); }
