@@ -74,6 +74,21 @@ def compress_with_model(hdr: bytes, pcomp: bytes, args, data: bytes, filename: s
     return out.raw[:n]
 
 
+def compress_segments(hdr: bytes, pcomp: bytes, data: bytes, cuts, dosha1: bool = True, with_tag: bool = True) -> bytes:
+    """One block whose segments are data[cuts[k]:cuts[k+1]] (names seg0, seg1, ..., comment = size), Compressor.cs:133-248."""
+    import numpy as np
+    off = np.asarray(cuts, dtype=np.uint64)
+    cap = len(data) * 2 + len(hdr) + len(pcomp) * 4 + 4096 + 64 * len(cuts)
+    out = C.create_string_buffer(cap)
+    L = lib()
+    L.orc_compress_segments.restype = C.c_int64
+    L.orc_compress_segments.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_uint64]
+    n = _check(L.orc_compress_segments(hdr, len(hdr), pcomp, len(pcomp), data, off.ctypes.data, len(cuts) - 1, 1 if dosha1 else 0,
+                                       1 if with_tag else 0, out, cap))
+    return out.raw[:n]
+
+
 def compress_block(data: bytes, method: str, filename: str | None = None, comment: str | None = None,
                    dosha1: bool = True) -> bytes:
     """LibZPAQ.compressBlock, LibZPAQ.cs:117-325."""

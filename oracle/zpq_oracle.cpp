@@ -1087,6 +1087,51 @@ static void compress_block(const U8* hdr, size_t hlen, const U8* pcomp, size_t p
   out.push_back(255);                                       // Compressor.cs:294-299
 }
 
+// One block with several segments, as a caller of the reference's Compressor writes it (Compressor.cs:133-146, 156-190, 193-248):
+// startBlock once (Encoder.init once, Compressor.cs:97), then per segment startSegment / compress / endSegment; the PCOMP preamble
+// goes into the first segment only (postProcess acts in state SEG1, :158), the arithmetic coder and the predictor carry on across
+// the segment ends.  No pre-processing (compressBlock, the only caller that pre-processes, writes one segment).
+static void compress_block_segments(const U8* hdr, size_t hlen, const U8* pcomp, size_t plen, const U8* in, const U64* seg_off,
+                                    unsigned nseg, int dosha1, int with_tag, Bytes& out) {
+  ZPAQL z;
+  ByteSource hs(hdr, hlen);
+  z.read(hs);
+  if (with_tag) out.insert(out.end(), kTag, kTag + 13);
+  out.push_back('z'); out.push_back('P'); out.push_back('Q');
+  out.push_back(1 + (z.header[6] == 0));
+  out.push_back(1);
+  z.write(out, false);
+  Encoder enc(z);
+  enc.out = &out;
+  enc.init();
+  for (unsigned k = 0; k < nseg; ++k) {
+    const U8* d = in + seg_off[k];
+    const size_t n = (size_t)(seg_off[k + 1] - seg_off[k]);
+    out.push_back(1);
+    const std::string name = "seg" + std::to_string(k);
+    out.insert(out.end(), name.begin(), name.end());
+    out.push_back(0);
+    const std::string cm = std::to_string(n);
+    out.insert(out.end(), cm.begin(), cm.end());
+    out.push_back(0);
+    out.push_back(0);
+    if (k == 0) {
+      if (plen > 0) {
+        enc.compress(1);
+        enc.compress((int)(plen & 255));
+        enc.compress((int)((plen >> 8) & 255));
+        for (size_t i = 0; i < plen; ++i) enc.compress(pcomp[i]);
+      } else enc.compress(0);
+    }
+    for (size_t i = 0; i < n; ++i) enc.compress(d[i]);
+    enc.compress(-1);
+    out.push_back(0); out.push_back(0); out.push_back(0); out.push_back(0);
+    if (dosha1) { U8 sha[20]; SHA1 s; s.write(d, (unsigned)n); s.result(sha); out.push_back(253); out.insert(out.end(), sha, sha + 20); }
+    else out.push_back(254);
+  }
+  out.push_back(255);
+}
+
 // Decompresser.cs:29-194 driven by LibZPAQ.decompress, LibZPAQ.cs:65-79.  Decodes every block
 // and segment in `arc`; appends output to `out`; verifies stored SHA-1s; returns the number of
 // blocks; sha_status (if not null) receives per segment 0=no checksum 1=match 2=mismatch.
@@ -1226,6 +1271,17 @@ int64_t orc_compress_block(const uint8_t* hdr, uint64_t hlen, const uint8_t* pco
   ORC_TRY
   orc::Bytes o;
   orc::compress_block(hdr, hlen, pcomp, plen, args9, in, n, filename, comment, dosha1, with_tag, o);
+  if (o.size() > cap) orc::fail("oracle: output buffer too small");
+  memcpy(out, o.data(), o.size());
+  return (int64_t)o.size();
+  ORC_CATCH
+}
+
+int64_t orc_compress_segments(const uint8_t* hdr, uint64_t hlen, const uint8_t* pcomp, uint64_t plen, const uint8_t* in,
+                              const uint64_t* seg_off, uint32_t nseg, int dosha1, int with_tag, uint8_t* out, uint64_t cap) {
+  ORC_TRY
+  orc::Bytes o;
+  orc::compress_block_segments(hdr, hlen, pcomp, plen, in, (const orc::U64*)seg_off, nseg, dosha1, with_tag, o);
   if (o.size() > cap) orc::fail("oracle: output buffer too small");
   memcpy(out, o.data(), o.size());
   return (int64_t)o.size();

@@ -9,7 +9,22 @@ open(out + "_raw.csv", "w").write(raw)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
                      capture_output=True, text=True, check=True).stdout
 lines, total, H, cur = [], collections.Counter(), None, None
-for r in csv.reader(io.StringIO(src)):
+def rows(text):
+    """ncu quotes every field but does not escape quotes inside source text (inline asm): split data rows from the right."""
+    ncol = None
+    for line in text.splitlines():
+        if not line.startswith('"'):
+            continue
+        if line.startswith('"Line No"') or line.startswith('"File Path"') or ncol is None:
+            r = next(csv.reader([line]))
+            if r and r[0] == "Line No": ncol = len(r)
+            yield r
+            continue
+        body = line[1:-1] if line.endswith('"') else line[1:]
+        parts = body.rsplit('","', ncol - 2)
+        first = parts[0].split('","', 1)
+        yield [first[0], first[1] if len(first) > 1 else ""] + parts[1:]
+for r in rows(src):
     if not r: continue
     if r[0] == "File Path": cur = r[1].split("/")[-1]; continue
     if r[0] == "Line No": H = r; continue

@@ -111,3 +111,20 @@ def test_block_memory_matches_reference_zpaql_memory(ref, what):
     assert z.block_memory(hdr) == want                      # the product's host code (no GPU needed)
     if what == ("level", 2):
         assert int(want) == 111424926
+
+
+@pytest.mark.parametrize("level", [1, 2, 3])
+def test_reference_decoder_restores_multi_segment_blocks(ref, level):
+    """Several segments in one block (Compressor.cs:133-146: startSegment after endSegment; Decompresser.cs:128-134: the decoder
+    and the post-processor are initialised for the first segment only): the reference's Decompresser text decodes what the
+    oracle's multi-segment writer produces, segment by segment, with every stored SHA-1."""
+    from oracle import frontend as fe
+    data = _data(90 + level, 9000)
+    hdr, _ = fe.builtin_model(level)
+    cuts = [0, 2500, 2500, 2501, 7000, 9000]                      # an empty and a one-byte segment among them
+    arc = po.compress_segments(bytes(hdr), b"", data, cuts)
+    n, out, marks = _ref_decompress(ref, arc, len(data) + 16)
+    assert n == len(data) and out == data
+    assert marks == [b"\x01" + po.sha1(data[cuts[k]:cuts[k + 1]]) for k in range(len(cuts) - 1)]
+    got, st = po.decompress(arc)
+    assert got == data and st == [1] * (len(cuts) - 1)
