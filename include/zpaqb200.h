@@ -157,7 +157,8 @@ int64_t zpq_find_blocks(const uint8_t* archive, uint64_t n, uint64_t* offsets, u
 /* LibZPAQ.decompress(in, out), LibZPAQ.cs:65-79, for nb archive blocks at once: block i is
  * in[in_off[i] .. in_off[i+1]) and may start at its locator tag or at "zPQ".  All segments of a
  * block are decoded and concatenated into out[out_off[i] .. out_off[i+1]).  sha1_status (may be
- * NULL) receives per block: 0 = no checksum stored, 1 = every stored SHA-1 matched, 2 = mismatch
+ * NULL) receives per block: 0 = no segment stores a checksum, 1 = the SHA-1 of every segment that stores one matched the
+ * restored bytes of that segment (hashed on the device), 2 = at least one did not
  * (Decompresser.readSegmentEnd, Decompresser.cs:163-194).  block_status (may be NULL) receives
  * ZPQ_BLOCK_* per block; a damaged block does not stop the batch, the call then returns
  * ZPQ_E_CORRUPT after decoding the others. */

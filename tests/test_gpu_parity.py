@@ -337,3 +337,63 @@ def test_level5_analysis_on_the_device_matches_oracle(gpu_ctx, oracle, zlib_):
         assert arc.tobytes() == ref
         out, _, sha, _ = gpu_ctx.decompress_blocks(arc, ooff)
         assert out.tobytes() == data and set(sha.tolist()) == {1}
+
+
+# ---- blocks with several segments (Compressor.cs:133-146; Decompresser.cs:128-134: decoder and post-processor start once per block) ----
+def _model(method):
+    from oracle import frontend as fe
+    if method in (1, 2, 3):
+        return bytes(fe.builtin_model(method)[0]), b"", [0] * 9
+    text, args = fe.make_config(method)
+    hdr, pcomp = fe.compile_config(text, args)[:2]
+    return bytes(hdr), bytes(pcomp), list(args)
+
+
+@pytest.mark.parametrize("method", [1, 2, 3, "x0,0c256,0,255,255", "x0,4c0,0,255", "x0,2,12,0,7,21,1c0,0,255", "x0,1,4,0,7,21,1", "x0,5,4,0,3,19"])
+def test_multi_segment_blocks_decode_and_verify_every_checksum(gpu_ctx, oracle, method):
+    from tools import synth
+    hdr, pcomp, args = _model(method)
+    data = synth.blocks("mixed", 1300, 1, 60000).tobytes()
+    cuts = [0, 9000, 9000, 9001, 30000, 60000]                 # an empty and a one-byte segment among them
+    parts = [data[cuts[k]:cuts[k + 1]] for k in range(len(cuts) - 1)]
+    # a segment carries its own transformed data (the programs restart at every end of segment, LibZPAQ.cs:465, :599, :805-812)
+    stream = [oracle.preprocess(p, args) if pcomp else p for p in parts]
+    cat = b"".join(stream)
+    scuts = np.concatenate([[0], np.cumsum([len(x) for x in stream])]).tolist()
+    arc = oracle.compress_segments(hdr, pcomp, cat, scuts, dosha1=False)
+    want, _ = oracle.decompress(arc, cap=1 << 20)
+    assert want == data
+    two = arc + oracle.compress_segments(hdr, pcomp, cat[:scuts[2]], scuts[:3], dosha1=False)
+    out, ooff, sha, bst = gpu_ctx.decompress_blocks(two, np.asarray([0, len(arc), len(two)], dtype=np.uint64))
+    assert out.tobytes() == data + data[:cuts[2]] and ooff.tolist() == [0, len(data), len(data) + cuts[2]] and not bst.any()
+    assert sha.tolist() == [0, 0]                               # nothing stored
+    if not pcomp:
+        # with checksums (they cover the segment's own bytes): all verified on the device; one damaged checksum is found
+        arc = oracle.compress_segments(hdr, pcomp, cat, scuts, dosha1=True)
+        out, ooff, sha, bst = gpu_ctx.decompress_blocks(arc, np.asarray([0, len(arc)], dtype=np.uint64))
+        assert out.tobytes() == data and sha.tolist() == [1]
+        bad = bytearray(arc)
+        bad[-3] ^= 1                                           # inside the last segment's stored SHA-1
+        out, ooff, sha, bst = gpu_ctx.decompress_blocks(bytes(bad), np.asarray([0, len(bad)], dtype=np.uint64))
+        assert out.tobytes() == data and sha.tolist() == [2]
+        k = arc.index(b"\x00\x00\x00\x00\xfd") + 7              # inside the FIRST segment's stored SHA-1
+        bad = bytearray(arc); bad[k] ^= 1
+        out, ooff, sha, bst = gpu_ctx.decompress_blocks(bytes(bad), np.asarray([0, len(bad)], dtype=np.uint64))
+        assert out.tobytes() == data and sha.tolist() == [2]
+
+
+def test_many_two_segment_blocks_cover_every_coder_state_at_a_segment_end(gpu_ctx, oracle):
+    """The arithmetic coder is initialised once per block (Encoder.init in startBlock, Decoder.init for the first segment only): after
+    the end-of-segment flag `low` is 0x100, 0x10000 or 0x1000000 instead of 1 about once in 256 segment ends, and a decoder that
+    started every segment afresh would lose the block there.  1500 small two-segment blocks meet that case with probability 0.997."""
+    from tools import synth
+    hdr, pcomp, args = _model(1)
+    nb = 1500
+    data = synth.blocks("mixed", 1400, 1, nb * 160).tobytes()
+    arcs = []
+    for i in range(nb):
+        part = data[i * 160:(i + 1) * 160]
+        arcs.append(oracle.compress_segments(hdr, b"", part, [0, 40 + i % 80, 160]))
+    offs = np.concatenate([[0], np.cumsum([len(a) for a in arcs])]).astype(np.uint64)
+    out, ooff, sha, bst = gpu_ctx.decompress_blocks(b"".join(arcs), offs)
+    assert out.tobytes() == data and set(sha.tolist()) == {1} and not bst.any()

@@ -786,6 +786,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
   std::vector<uint32_t> pending;
   for (uint32_t i = b0; i < b1; ++i) if (bstat[i] == ZPQ_BLOCK_OK) pending.push_back(i);
   std::vector<uint64_t> slot_off(nbr + 1, 0);
+  std::vector<std::vector<uint64_t>> seg_out(nbr);      // restored bytes of a block at the end of each of its segments
   uint32_t launches = 0;
   double codec_ms = 0, post_ms = 0;
   uint32_t post_native = 0, post_interp = 0;
@@ -862,7 +863,8 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         const uint64_t o_jobs = place(sizeof(DecJob) * jobs.size()), o_segs = place(sizeof(DecSeg) * nseg), o_send = place(8ull * nseg),
                        o_pjobs = place(sizeof(PostJob) * jobs.size()), o_raw = place(sizeof(BlockResult) * jobs.size()),
                        o_res = place(sizeof(BlockResult) * jobs.size()), o_queue = place(512), o_kind = place(4ull * jobs.size()),
-                       o_cand = place(sizeof(PostCand) * std::max<size_t>(dcands.size(), 1)), o_cbytes = place(cand_bytes.size() + 16);
+                       o_cand = place(sizeof(PostCand) * std::max<size_t>(dcands.size(), 1)), o_cbytes = place(cand_bytes.size() + 16),
+                       o_sout = place(8ull * nseg);
         d.meta.reserve(mo);
         uint8_t* meta = d.meta.as<uint8_t>();
         d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
@@ -877,6 +879,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
           CU(cudaMemcpyAsync(meta + o_cbytes, cand_bytes.data(), cand_bytes.size(), cudaMemcpyHostToDevice, s));
         }
         CU(cudaMemsetAsync(meta + o_queue, 0, 512, s));
+        CU(cudaMemsetAsync(meta + o_sout, 0, 8ull * nseg, s));
         CodecParams P{};
         P.plan = d.plan.as<Plan>(); P.tab = d.d_tab;
         P.arenas = d.arena.as<uint8_t>(); P.arena_stride = L.plan->arena_bytes;
@@ -895,7 +898,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
           Q.raw = d.work.as<uint8_t>(); Q.djobs = P.djobs; Q.seg_end = P.seg_end; Q.raw_results = (const BlockResult*)(meta + o_raw);
           Q.out = d.slots.as<uint8_t>(); Q.pjobs = (const PostJob*)(meta + o_pjobs); Q.results = (BlockResult*)(meta + o_res);
           Q.njobs = P.njobs; Q.resident = L.resident; Q.queue = (uint32_t*)(meta + o_queue + 256); Q.queue2 = (uint32_t*)(meta + o_queue + 128);
-          Q.jobkind = (uint32_t*)(meta + o_kind);
+          Q.jobkind = (uint32_t*)(meta + o_kind); Q.seg_out_end = (uint64_t*)(meta + o_sout);
           Q.cand_bytes = meta + o_cbytes; Q.cands = (const PostCand*)(meta + o_cand); Q.ncand = (uint32_t)dcands.size();
           Q.has_bwt = has_bwt ? 1u : 0u; Q.max_raw = max_raw;
           d.t_post.start(s);
@@ -907,6 +910,8 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         }
         std::vector<BlockResult> r(jobs.size());
         std::vector<uint32_t> kinds(jobs.size());
+        std::vector<uint64_t> sout(nseg, 0);
+        CU(cudaMemcpyAsync(sout.data(), meta + o_sout, 8ull * nseg, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(r.data(), meta + o_res, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(kinds.data(), meta + o_kind, 4ull * jobs.size(), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
@@ -915,7 +920,10 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         post_ms += d.t_post.ms();
         d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
         snprintf(d.stats.kernel, sizeof d.stats.kernel, "%s", L.kernel.c_str());
-        for (size_t k = 0; k < ids.size(); ++k) res[ids[k] - b0] = r[k];
+        for (size_t k = 0; k < ids.size(); ++k) {
+          res[ids[k] - b0] = r[k];
+          seg_out[ids[k] - b0].assign(sout.begin() + jobs[k].seg_first, sout.begin() + jobs[k].seg_first + jobs[k].seg_count);
+        }
       } catch (const Failure& f) {
         // a header this build cannot run (or that does not fit) takes its own blocks down, not the batch
         if (f.code == ZPQ_E_CUDA) throw;
@@ -929,7 +937,8 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
     pending.swap(again);
   }
   for (uint32_t i : pending) res[i - b0].status = ZPQ_BLOCK_OVERFLOW;
-  // ---- SHA-1 of every block's output when a checksum is stored (single-segment blocks) ----
+  // ---- SHA-1 of every SEGMENT's restored bytes, compared with the one stored behind the segment (Decompresser.readSegmentEnd,
+  //      Decompresser.cs:163-194; LibZPAQ.decompress hashes per segment, LibZPAQ.cs:70-76) ----
   for (uint32_t i = b0; i < b1; ++i) {
     if (bstat[i] != ZPQ_BLOCK_OK) continue;
     bstat[i] = (uint8_t)res[i - b0].status;
@@ -937,36 +946,53 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
     else fail_block(i, (uint8_t)res[i - b0].status, "failed to decode (status " + std::to_string(res[i - b0].status) + ")");
   }
   {
+    std::vector<uint64_t> h_soff;       // one range per segment that stores a checksum
+    std::vector<uint32_t> h_slen, h_sblk, h_sseg;
+    for (uint32_t i = 0; i < nbr; ++i) {
+      if (bstat[b0 + i] != ZPQ_BLOCK_OK) continue;
+      const auto& segs = blocks[b0 + i].ref.segs;
+      const auto& ends = seg_out[i];
+      uint64_t prev = 0;
+      for (size_t k = 0; k < segs.size() && k < ends.size(); ++k) {
+        const uint64_t end = std::min<uint64_t>(std::max(ends[k], prev), lens[b0 + i]);
+        if (segs[k].has_sha1) { h_soff.push_back(slot_off[i] + prev); h_slen.push_back((uint32_t)(end - prev)); h_sblk.push_back(i); h_sseg.push_back((uint32_t)k); }
+        prev = end;
+      }
+    }
+    const uint32_t nsha = (uint32_t)h_soff.size();
     uint64_t mo = 0;
     auto place = [&](uint64_t bytes) { uint64_t o = mo; mo = align_up(mo + bytes, 256); return o; };
-    const uint64_t o_slot = place(8ull * (nbr + 1)), o_len64 = place(8ull * nbr), o_len32 = place(4ull * nbr),
-                   o_foff = place(8ull * (nbr + 1)), o_dig = place(20ull * nbr);
+    const uint64_t o_slot = place(8ull * (nbr + 1)), o_len64 = place(8ull * nbr), o_foff = place(8ull * (nbr + 1)),
+                   o_soff = place(8ull * std::max(nsha, 1u)), o_slen = place(4ull * std::max(nsha, 1u)), o_dig = place(20ull * std::max(nsha, 1u));
     d.meta.reserve(mo);
     uint8_t* meta = d.meta.as<uint8_t>();
-    std::vector<uint32_t> len32(nbr);
     std::vector<uint64_t> len64(nbr);
     uint64_t max_len = 0, total = 0;
-    for (uint32_t i = 0; i < nbr; ++i) { len64[i] = lens[b0 + i]; len32[i] = (uint32_t)len64[i]; max_len = std::max(max_len, len64[i]); total += len64[i]; }
+    for (uint32_t i = 0; i < nbr; ++i) { len64[i] = lens[b0 + i]; max_len = std::max(max_len, len64[i]); total += len64[i]; }
     reserve_io(d.slots, 16, d.arena);
     CU(cudaMemcpyAsync(meta + o_slot, slot_off.data(), 8ull * (nbr + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(meta + o_len64, len64.data(), 8ull * nbr, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(meta + o_len32, len32.data(), 4ull * nbr, cudaMemcpyHostToDevice, s));
-    CU(launch_sha1(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint32_t*)(meta + o_len32), nbr, meta + o_dig, s));
+    if (nsha) {
+      CU(cudaMemcpyAsync(meta + o_soff, h_soff.data(), 8ull * nsha, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(meta + o_slen, h_slen.data(), 4ull * nsha, cudaMemcpyHostToDevice, s));
+      CU(launch_sha1(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_soff), (const uint32_t*)(meta + o_slen), nsha, meta + o_dig, s));
+    }
     CU(launch_scan((const uint64_t*)(meta + o_len64), (uint64_t*)(meta + o_foff), nbr, s));
     reserve_io(d.out, std::max<uint64_t>(total, 16), d.arena);
     CU(launch_gather(d.slots.as<uint8_t>(), (const uint64_t*)(meta + o_slot), (const uint64_t*)(meta + o_len64),
                      d.out.as<uint8_t>(), (const uint64_t*)(meta + o_foff), d.out.cap, nbr, max_len, s));
     launches += 3;
     d.t_kern.stop(s);
-    std::vector<uint8_t> dig(20ull * nbr);
-    CU(cudaMemcpyAsync(dig.data(), meta + o_dig, 20ull * nbr, cudaMemcpyDeviceToHost, s));
+    std::vector<uint8_t> dig(20ull * std::max(nsha, 1u));
+    if (nsha) CU(cudaMemcpyAsync(dig.data(), meta + o_dig, 20ull * nsha, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    for (uint32_t i = 0; i < nbr; ++i) {
-      uint8_t st = 0;
-      const auto& segs = blocks[b0 + i].ref.segs;
-      if (bstat[b0 + i] == ZPQ_BLOCK_OK && segs.size() == 1 && segs[0].has_sha1)
-        st = memcmp(segs[0].sha1, &dig[20ull * i], 20) == 0 ? 1 : 2;
-      sha[b0 + i] = st;
+    // per block: 0 = no checksum stored, 1 = every stored checksum matched, 2 = at least one did not
+    for (uint32_t i = 0; i < nbr; ++i) sha[b0 + i] = 0;
+    for (uint32_t q = 0; q < nsha; ++q) {
+      const uint32_t i = h_sblk[q];
+      const bool same = memcmp(blocks[b0 + i].ref.segs[h_sseg[q]].sha1, &dig[20ull * q], 20) == 0;
+      if (!same) sha[b0 + i] = 2;
+      else if (sha[b0 + i] == 0) sha[b0 + i] = 1;
     }
     R.total = total;
   }

@@ -642,6 +642,7 @@ __global__ void __launch_bounds__(256) k_post(const PostParams Q) {
         if (n > O.out_cap) status = ZPQ_BLOCK_OVERFLOW;
         else for (uint64_t i = lane; i < n; i += 32) out[i] = raw[1 + i];
         opos = n;
+        if (lane == 0) for (uint32_t k = 0; k < J.seg_count; ++k) Q.seg_out_end[J.seg_first + k] = send[k] - 1;
       } else if (raw[0] == 1) {
         uint32_t psize = 0;
         if (e0 < 3) status = ZPQ_BLOCK_POSTPROC;
@@ -676,6 +677,7 @@ __global__ void __launch_bounds__(256) k_post(const PostParams Q) {
               for (; pos < end; ++pos)
                 if (zpaql_run(pvm, penv, raw[pos], budget)) { status = ZPQ_BLOCK_ZPAQL; break; }
               if (status == ZPQ_BLOCK_OK && zpaql_run(pvm, penv, 0xFFFFFFFFu, budget)) status = ZPQ_BLOCK_ZPAQL;
+              Q.seg_out_end[J.seg_first + sg] = penv.out_pos;
             }
             opos = penv.out_pos;
           }

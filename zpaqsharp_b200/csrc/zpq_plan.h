@@ -201,6 +201,7 @@ struct PostParams {
   const uint8_t* raw;         // what the decoder wrote: per job at djobs[j].out_off
   const DecJob* djobs;
   const uint64_t* seg_end;
+  uint64_t* seg_out_end;      // restored bytes of the block at the end of every segment (parallel to seg_end): the ranges the stored SHA-1s cover
   const BlockResult* raw_results;
   uint8_t* out;               // restored bytes: per job at pjobs[j].out_off
   const PostJob* pjobs;

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) k_post_pass(const PostParams Q) {
   if (blockIdx.y == 0 && threadIdx.x == 0) {
     Q.results[job].out_len = n;
     Q.results[job].status = n > O.out_cap ? ZPQ_BLOCK_OVERFLOW : ZPQ_BLOCK_OK;
+    for (uint32_t k = 0; k < J.seg_count; ++k) Q.seg_out_end[J.seg_first + k] = Q.seg_end[J.seg_first + k] - 1;
   }
   if (n > O.out_cap) return;
   const uint64_t begin = (uint64_t)blockIdx.y * kPassChunk;
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(128) k_post_lz(const PostParams Q) {
     if (rc == LZ_OK && (e8 || kind == PK_E8E9)) un_e8e9(M, produced, lane);
     opos += produced;
     pos = end;
+    if (lane == 0) Q.seg_out_end[Q.djobs[job].seg_first + sg] = opos;
   }
   __syncwarp();
   if (lane == 0) {
@@ -421,7 +423,10 @@ __global__ void __launch_bounds__(kBwtThreads) k_post_bwt(const PostParams Q) {
       __syncthreads();
       if (e8 && warp == 0) un_e8e9(r.out, total, lane);
     }
-    if (tid == 0) { Q.results[job].out_len = total; Q.results[job].status = total > r.cap ? ZPQ_BLOCK_OVERFLOW : ZPQ_BLOCK_OK; }
+    if (tid == 0) {
+      Q.results[job].out_len = total; Q.results[job].status = total > r.cap ? ZPQ_BLOCK_OVERFLOW : ZPQ_BLOCK_OK;
+      Q.seg_out_end[Q.djobs[job].seg_first] = total;
+    }
   }
 }
 
