@@ -51,15 +51,15 @@ def bwt_method(a0): return "x%d,3ci1" % a0                                      
 # max_blocks bounds the batch of the non-headline configs so that the default run stays within minutes.
 CONFIGS = {
     "C1": {"what": "configs[0]: single order-2 CM, method x0,0c256,0,255,255, 1,044,480-byte blocks of synthetic text",
-           "kind": "text", "block": BLOCK, "how": ("method", "x0,0c256,0,255,255"), "max_blocks": 2048,
+           "kind": "text", "block": BLOCK, "how": ("method", "x0,0c256,0,255,255"), "max_blocks": 2960,
            "metric": "compress MB/s, order-2 CM 1 MB blocks, byte-exact"},
     "C2a": {"what": "BASELINE configs[1]: mid.cfg (Compressor.startBlock(2)), 1,044,480-byte blocks of the 8192-block (8 GB) synthetic mixed text/binary stream",
             "kind": "mixed", "block": BLOCK, "how": ("level", 2), "max_blocks": 148 * 16, "metric": METRIC},
     "C2b": {"what": "configs[1] read literally: libzpaq method 20 = x0,1,4,0,7,21,1 (bit-packed LZ77, suffix-array matcher, stored), 1 MB mixed blocks",
-            "kind": "mixed", "block": BLOCK, "how": ("method", lz_method(0)), "max_blocks": 592,
+            "kind": "mixed", "block": BLOCK, "how": ("method", lz_method(0)), "max_blocks": 1776,
             "metric": "compress MB/s, method 20 (LZ77 stored) 1 MB blocks, byte-exact"},
     "C2c": {"what": "configs[1]'s parenthesis: x0,2,12,0,7,21,1c0,0,511i2m (byte LZ77 + ICM/ISSE chain + MIX), 1 MB mixed blocks",
-            "kind": "mixed", "block": BLOCK, "how": ("method", lzcm_method(0)), "max_blocks": 592,
+            "kind": "mixed", "block": BLOCK, "how": ("method", lzcm_method(0)), "max_blocks": 1776,
             "metric": "compress MB/s, LZ77+ICM/ISSE+MIX 1 MB blocks, byte-exact"},
     "C3": {"what": "configs[2]: method 32,128,1 = x2,3ci1 (BWT + ICM/ISSE), 4,190,208-byte blocks of synthetic text",
            "kind": "text", "block": BLOCK_4MB, "how": ("method", bwt_method(2)), "max_blocks": 592,

@@ -364,7 +364,8 @@ def test_multi_segment_blocks_decode_and_verify_every_checksum(gpu_ctx, oracle, 
     want, _ = oracle.decompress(arc, cap=1 << 20)
     assert want == data
     two = arc + oracle.compress_segments(hdr, pcomp, cat[:scuts[2]], scuts[:3], dosha1=False)
-    out, ooff, sha, bst = gpu_ctx.decompress_blocks(two, np.asarray([0, len(arc), len(two)], dtype=np.uint64))
+    # (the comments of these segments give the size of the TRANSFORMED data: the caller sizes the output itself)
+    out, ooff, sha, bst = gpu_ctx.decompress_blocks(two, np.asarray([0, len(arc), len(two)], dtype=np.uint64), out=np.empty(1 << 20, dtype=np.uint8))
     assert out.tobytes() == data + data[:cuts[2]] and ooff.tolist() == [0, len(data), len(data) + cuts[2]] and not bst.any()
     assert sha.tolist() == [0, 0]                               # nothing stored
     if not pcomp:
