@@ -1313,34 +1313,77 @@ int zpq_compress_blocks(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off,
     std::vector<int> gaps;
     const bool analyse = method_needs_analysis(method);
     if (analyse) device_gap_histograms(ctx, in, in_off, nb, gaps);
-    while (i < nb) {
-      auto derive = [&](uint32_t b, Model& M) {
-        const uint64_t n = in_off[b + 1] - in_off[b];
-        std::string x = expand_method_gaps(method, n, analyse ? gaps.data() + (size_t)b * kGapBins : nullptr);
-        std::string cfg = make_config(x, M.args);
-        Bytes h;
-        compile_config(cfg, M.args, h, M.pcomp, nullptr);
-        parse_header(h.data(), h.size(), M.hdr);
-      };
-      Model M;
-      derive(i, M);
-      uint32_t j = i + 1;
-      for (; j < nb; ++j) {
-        Model N;
-        derive(j, N);
-        if (N.hdr.wire != M.hdr.wire || N.pcomp != M.pcomp || memcmp(N.args, M.args, sizeof(M.args)) != 0) break;
+    // derive each block's model (LibZPAQ.cs:128-300)
+    std::vector<Model> models(nb);
+    for (uint32_t b = 0; b < nb; ++b) {
+      Model& M = models[b];
+      const uint64_t n = in_off[b + 1] - in_off[b];
+      std::string x = expand_method_gaps(method, n, analyse ? gaps.data() + (size_t)b * kGapBins : nullptr);
+      std::string cfg = make_config(x, M.args);
+      Bytes h;
+      compile_config(cfg, M.args, h, M.pcomp, nullptr);
+      parse_header(h.data(), h.size(), M.hdr);
+    }
+    auto same_model = [&](uint32_t a, uint32_t b) {
+      return models[a].hdr.wire == models[b].hdr.wire && models[a].pcomp == models[b].pcomp && memcmp(models[a].args, models[b].args, sizeof(models[a].args)) == 0;
+    };
+    auto names = [&](uint32_t b, std::vector<std::string>& fn, std::vector<std::string>& cm) {
+      const uint64_t n = in_off[b + 1] - in_off[b];
+      fn.push_back(b == 0 && filename0 ? filename0 : "");
+      std::string c = std::to_string(n);                       // LibZPAQ.cs:298-299
+      if (b == 0 && comment0 && *comment0) c += std::string(" ") + comment0;
+      cm.push_back(c);
+    };
+    // blocks of one model form one device batch: runs of consecutive blocks where that is all there is ...
+    uint32_t runs = 0;
+    std::vector<uint32_t> rep;                                  // first block of every distinct model
+    std::vector<uint32_t> cls(nb, 0);
+    for (uint32_t b = 0; b < nb; ++b) {
+      if (b == 0 || !same_model(b, b - 1)) ++runs;
+      uint32_t k = 0;
+      while (k < rep.size() && !same_model(rep[k], b)) ++k;
+      if (k == rep.size()) rep.push_back(b);
+      cls[b] = k;
+    }
+    if (runs == rep.size()) {
+      while (i < nb) {
+        uint32_t j = i + 1;
+        while (j < nb && same_model(i, j)) ++j;
+        std::vector<std::string> fn, cm;
+        for (uint32_t b = i; b < j; ++b) names(b, fn, cm);
+        compress_model(ctx, models[i], in, in_off, i, j - i, fn, cm, dosha1 != 0, true, out, out_cap, base, out_off);
+        base = out_off[j];
+        i = j;
       }
+      return;
+    }
+    // ... and otherwise (data-dependent models of levels 5..9, ragged block sizes: the same model comes back after other
+    // models) all blocks of a model, gathered on the host, so that a batch is as large as it can be; the archive blocks go
+    // back into block order
+    std::vector<Bytes> arcs(nb);
+    for (uint32_t k = 0; k < rep.size(); ++k) {
+      std::vector<uint32_t> ids;
+      for (uint32_t b = 0; b < nb; ++b) if (cls[b] == k) ids.push_back(b);
+      Bytes gin;
+      std::vector<uint64_t> goff(ids.size() + 1, 0);
       std::vector<std::string> fn, cm;
-      for (uint32_t b = i; b < j; ++b) {
-        const uint64_t n = in_off[b + 1] - in_off[b];
-        fn.push_back(b == 0 && filename0 ? filename0 : "");
-        std::string c = std::to_string(n);                       // LibZPAQ.cs:298-299
-        if (b == 0 && comment0 && *comment0) c += std::string(" ") + comment0;
-        cm.push_back(c);
+      for (size_t t = 0; t < ids.size(); ++t) {
+        const uint32_t bb = ids[t];
+        gin.insert(gin.end(), in + in_off[bb], in + in_off[bb + 1]);
+        goff[t + 1] = gin.size();
+        names(bb, fn, cm);
       }
-      compress_model(ctx, M, in, in_off, i, j - i, fn, cm, dosha1 != 0, true, out, out_cap, base, out_off);
-      base = out_off[j];
-      i = j;
+      gin.resize(gin.size() + 64);
+      Bytes gout(gin.size() + gin.size() / 4 + (models[rep[k]].hdr.wire.size() + models[rep[k]].pcomp.size() * 4 + 70000) * ids.size());
+      std::vector<uint64_t> gooff(ids.size() + 1, 0);
+      compress_model(ctx, models[rep[k]], gin.data(), goff.data(), 0, (uint32_t)ids.size(), fn, cm, dosha1 != 0, true, gout.data(), gout.size(), 0, gooff.data());
+      for (size_t t = 0; t < ids.size(); ++t) arcs[ids[t]].assign(gout.begin() + gooff[t], gout.begin() + gooff[t + 1]);
+    }
+    for (uint32_t b = 0; b < nb; ++b) {
+      if (base + arcs[b].size() > out_cap) throw Failure(ZPQ_E_OUTPUT, "output buffer too small");
+      memcpy(out + base, arcs[b].data(), arcs[b].size());
+      base += arcs[b].size();
+      out_off[b + 1] = base;
     }
   });
 }
