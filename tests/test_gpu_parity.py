@@ -398,3 +398,32 @@ def test_many_two_segment_blocks_cover_every_coder_state_at_a_segment_end(gpu_ct
     offs = np.concatenate([[0], np.cumsum([len(a) for a in arcs])]).astype(np.uint64)
     out, ooff, sha, bst = gpu_ctx.decompress_blocks(b"".join(arcs), offs)
     assert out.tobytes() == data and set(sha.tolist()) == {1} and not bst.any()
+
+
+def test_mixed_method_archive_in_one_call(gpu_ctx, oracle, zlib_):
+    """blocks of different models interleaved in one batch.  The groups (one per model header) are decoded side by
+    side on their own streams; results come back in block order; a damaged block takes down neither its group nor the others."""
+    from tools import synth
+    methods = [2, "x0,1,4,0,7,21,1", "x0,2,12,0,7,21,1c0,0,511i2m", "x0,3ci1", 1, "x0,0c256,0,255,255"]
+    parts, arcs = [], []
+    for i in range(18):
+        m = methods[i % len(methods)]
+        d = synth.blocks("mixed" if i % 2 else "text", 1500 + i, 1, 20000 + 1000 * i).tobytes()
+        parts.append(d)
+        arcs.append(oracle.compress_block_level(d, m) if isinstance(m, int) else oracle.compress_block(d, m))
+    offs = np.concatenate([[0], np.cumsum([len(a) for a in arcs])]).astype(np.uint64)
+    out, ooff, sha, bst = gpu_ctx.decompress_blocks(b"".join(arcs), offs)
+    assert out.tobytes() == b"".join(parts) and set(sha.tolist()) == {1} and not bst.any()
+    assert ooff.tolist() == np.concatenate([[0], np.cumsum([len(p) for p in parts])]).tolist()
+    bad = [bytearray(a) for a in arcs]
+    bad[6][len(bad[6]) // 2] ^= 0x77                            # a mid.cfg block
+    with pytest.raises(zlib_.ZpaqError) as e:
+        gpu_ctx.decompress_blocks(b"".join(bytes(a) for a in bad), offs)
+    assert e.value.code == zlib_.E_CORRUPT and [i for i, s in enumerate(e.value.block_status) if s] == [6]
+    # the library's own compressor on the same ragged mix of sizes: one call per method, archives equal the oracle's
+    for m in methods[1:4]:
+        idx = [i for i in range(18) if methods[i % len(methods)] == m]
+        data = b"".join(parts[i] for i in idx)
+        o2 = np.concatenate([[0], np.cumsum([len(parts[i]) for i in idx])]).astype(np.uint64)
+        arc, _ = gpu_ctx.compress_blocks(data, o2, m)
+        assert arc.tobytes() == b"".join(arcs[i] for i in idx)

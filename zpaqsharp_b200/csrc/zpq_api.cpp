@@ -90,9 +90,23 @@ struct Timer {
   double ms() const { float t = 0; cudaEventElapsedTime(&t, a, b); return t; }
 };
 
+// What one group (one model header) of a decode batch owns while it runs: groups of different models run side by side, each on
+// its own stream with its own raw-stream buffer, job tables, plan and state arenas.
+struct Scratch {
+  DevBuf work, meta, plan, arena;
+  cudaStream_t stream = nullptr;
+  Timer t_codec, t_post;
+  void init() { CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); t_codec.init(); t_post.init(); }
+  void release() { work.release(); meta.release(); plan.release(); arena.release(); }
+  void fini() { release(); t_codec.fini(); t_post.fini(); if (stream) cudaStreamDestroy(stream); stream = nullptr; }
+};
+struct GroupBufs { DevBuf& work; DevBuf& meta; DevBuf& plan; DevBuf& arena; cudaStream_t stream; Timer& t_codec; Timer& t_post; };
+
 struct Device {
   int id = 0;
   cudaStream_t own = nullptr, stream = nullptr;
+  std::vector<std::unique_ptr<Scratch>> pool;      // for the second, third ... group of a decode batch
+  cudaEvent_t ev_ready = nullptr;
   int sms = 0;
   uint32_t smem_optin = 0;
   Tables* d_tab = nullptr;
@@ -115,11 +129,15 @@ struct Device {
     CU(cudaMalloc(&d_tab, sizeof(Tables)));
     CU(cudaMemcpy(d_tab, t.get(), sizeof(Tables), cudaMemcpyHostToDevice));
     t_all.init(); t_h2d.init(); t_kern.init(); t_codec.init(); t_d2h.init(); t_post.init();
+    CU(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
   }
   void fini() {
     cudaSetDevice(id);
     arena.release(); in.release(); work.release(); pre.release(); slots.release(); out.release(); meta.release(); plan.release();
     if (d_tab) cudaFree(d_tab);
+    for (auto& sc : pool) sc->fini();
+    pool.clear();
+    if (ev_ready) cudaEventDestroy(ev_ready);
     t_all.fini(); t_h2d.fini(); t_kern.fini(); t_codec.fini(); t_d2h.fini(); t_post.fini();
     if (own) cudaStreamDestroy(own);
   }
@@ -787,7 +805,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
   for (uint32_t i = b0; i < b1; ++i) if (bstat[i] == ZPQ_BLOCK_OK) pending.push_back(i);
   std::vector<uint64_t> slot_off(nbr + 1, 0);
   std::vector<std::vector<uint64_t>> seg_out(nbr);      // restored bytes of a block at the end of each of its segments
-  uint32_t launches = 0;
+  std::atomic<uint32_t> launches{0};
   double codec_ms = 0, post_ms = 0;
   uint32_t post_native = 0, post_interp = 0;
   d.t_kern.start(s);
@@ -821,15 +839,15 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
     // group by header bytes
     std::map<Bytes, std::vector<uint32_t>> groups;
     for (uint32_t i : pending) groups[blocks[i].ref.hdr.wire].push_back(i);
-    for (auto& g : groups) {
-      const std::vector<uint32_t>& ids = g.second;
+    std::mutex alloc_mu, res_mu;
+    auto run_group = [&](const std::vector<uint32_t>& ids, GroupBufs G) {
       const Header& hdr = blocks[ids[0]].ref.hdr;
       try {
         std::vector<DecJob> jobs(ids.size());
         std::vector<PostJob> pjobs(ids.size());
         std::vector<DecSeg> segs;
         // every decoder leaves the raw model stream -- PCOMP preamble (<= 64 KB + 3) + transformed data (LZ77 output may
-        // exceed the data by 1/16) -- in d.work; the post-processing pass turns it into the restored bytes in the slots
+        // exceed the data by 1/16) -- in G.work; the post-processing pass turns it into the restored bytes in the slots
         uint64_t raw_total = 0, max_raw = 0;
         for (size_t k = 0; k < ids.size(); ++k) {
           const DecBlock& b = blocks[ids[k]];
@@ -842,7 +860,8 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
           raw_total = align_up(raw_total + jobs[k].out_cap, 16);
           for (const SegmentRef& sg : b.ref.segs) segs.push_back(DecSeg{b.start - in_base + sg.data_off, sg.data_len});
         }
-        reserve_io(d.work, std::max<uint64_t>(raw_total, 16) + 64, d.arena);       // before the arenas are sized
+        std::unique_lock<std::mutex> alloc_lk(alloc_mu);    // groups size and take their memory one after the other, then run side by side
+        reserve_io(G.work, std::max<uint64_t>(raw_total, 16) + 64, G.arena);       // before the arenas are sized
         std::vector<PostCandidate> cands;
         post_candidates(hdr.ph, hdr.pm, cands);
         std::vector<PostCand> dcands(cands.size());
@@ -854,7 +873,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
           has_bwt = has_bwt || cands[k].kind == PK_BWT;
         }
         Launch L;
-        const uint64_t fr = free_device_memory() + d.arena.cap;
+        const uint64_t fr = free_device_memory() + G.arena.cap;
         const uint64_t reserve = 512ull << 20;
         plan_launch(d, hdr, true, ids.size(), fr > reserve ? fr - reserve : 0, ctx->max_resident, L, false, false, want_fast_decode(), max_raw);
         uint64_t mo = 0;
@@ -865,59 +884,61 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
                        o_res = place(sizeof(BlockResult) * jobs.size()), o_queue = place(512), o_kind = place(4ull * jobs.size()),
                        o_cand = place(sizeof(PostCand) * std::max<size_t>(dcands.size(), 1)), o_cbytes = place(cand_bytes.size() + 16),
                        o_sout = place(8ull * nseg);
-        d.meta.reserve(mo);
-        uint8_t* meta = d.meta.as<uint8_t>();
-        d.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
-        d.plan.reserve(sizeof(Plan));
-        CU(cudaMemcpyAsync(d.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
-                           cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(meta + o_jobs, jobs.data(), sizeof(DecJob) * jobs.size(), cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(meta + o_pjobs, pjobs.data(), sizeof(PostJob) * jobs.size(), cudaMemcpyHostToDevice, s));
-        if (!segs.empty()) CU(cudaMemcpyAsync(meta + o_segs, segs.data(), sizeof(DecSeg) * segs.size(), cudaMemcpyHostToDevice, s));
+        G.meta.reserve(mo);
+        uint8_t* meta = G.meta.as<uint8_t>();
+        G.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
+        G.plan.reserve(sizeof(Plan));
+        alloc_lk.unlock();
+        CU(cudaMemcpyAsync(G.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
+                           cudaMemcpyHostToDevice, G.stream));
+        CU(cudaMemcpyAsync(meta + o_jobs, jobs.data(), sizeof(DecJob) * jobs.size(), cudaMemcpyHostToDevice, G.stream));
+        CU(cudaMemcpyAsync(meta + o_pjobs, pjobs.data(), sizeof(PostJob) * jobs.size(), cudaMemcpyHostToDevice, G.stream));
+        if (!segs.empty()) CU(cudaMemcpyAsync(meta + o_segs, segs.data(), sizeof(DecSeg) * segs.size(), cudaMemcpyHostToDevice, G.stream));
         if (!dcands.empty()) {
-          CU(cudaMemcpyAsync(meta + o_cand, dcands.data(), sizeof(PostCand) * dcands.size(), cudaMemcpyHostToDevice, s));
-          CU(cudaMemcpyAsync(meta + o_cbytes, cand_bytes.data(), cand_bytes.size(), cudaMemcpyHostToDevice, s));
+          CU(cudaMemcpyAsync(meta + o_cand, dcands.data(), sizeof(PostCand) * dcands.size(), cudaMemcpyHostToDevice, G.stream));
+          CU(cudaMemcpyAsync(meta + o_cbytes, cand_bytes.data(), cand_bytes.size(), cudaMemcpyHostToDevice, G.stream));
         }
-        CU(cudaMemsetAsync(meta + o_queue, 0, 512, s));
-        CU(cudaMemsetAsync(meta + o_sout, 0, 8ull * nseg, s));
+        CU(cudaMemsetAsync(meta + o_queue, 0, 512, G.stream));
+        CU(cudaMemsetAsync(meta + o_sout, 0, 8ull * nseg, G.stream));
         CodecParams P{};
-        P.plan = d.plan.as<Plan>(); P.tab = d.d_tab;
-        P.arenas = d.arena.as<uint8_t>(); P.arena_stride = L.plan->arena_bytes;
-        P.in = d.in.as<uint8_t>(); P.out = d.work.as<uint8_t>();
+        P.plan = G.plan.as<Plan>(); P.tab = d.d_tab;
+        P.arenas = G.arena.as<uint8_t>(); P.arena_stride = L.plan->arena_bytes;
+        P.in = d.in.as<uint8_t>(); P.out = G.work.as<uint8_t>();
         P.djobs = (const DecJob*)(meta + o_jobs); P.segs = (const DecSeg*)(meta + o_segs);
         P.seg_end = (uint64_t*)(meta + o_send);
         P.results = (BlockResult*)(meta + o_raw);
         P.njobs = (uint32_t)jobs.size(); P.resident = L.resident; P.queue = (uint32_t*)(meta + o_queue); P.sm = L.sm;
-        d.t_codec.start(s);
-        CU(launch_codec(L, P, true, s));
-        d.t_codec.stop(s);
+        G.t_codec.start(s);
+        CU(launch_codec(L, P, true, G.stream));
+        G.t_codec.stop(s);
         ++launches;
         {
           PostParams Q{};
-          Q.plan = d.plan.as<Plan>(); Q.arenas = d.arena.as<uint8_t>(); Q.arena_stride = L.plan->arena_bytes;
-          Q.raw = d.work.as<uint8_t>(); Q.djobs = P.djobs; Q.seg_end = P.seg_end; Q.raw_results = (const BlockResult*)(meta + o_raw);
+          Q.plan = G.plan.as<Plan>(); Q.arenas = G.arena.as<uint8_t>(); Q.arena_stride = L.plan->arena_bytes;
+          Q.raw = G.work.as<uint8_t>(); Q.djobs = P.djobs; Q.seg_end = P.seg_end; Q.raw_results = (const BlockResult*)(meta + o_raw);
           Q.out = d.slots.as<uint8_t>(); Q.pjobs = (const PostJob*)(meta + o_pjobs); Q.results = (BlockResult*)(meta + o_res);
           Q.njobs = P.njobs; Q.resident = L.resident; Q.queue = (uint32_t*)(meta + o_queue + 256); Q.queue2 = (uint32_t*)(meta + o_queue + 128);
           Q.jobkind = (uint32_t*)(meta + o_kind); Q.seg_out_end = (uint64_t*)(meta + o_sout);
           Q.cand_bytes = meta + o_cbytes; Q.cands = (const PostCand*)(meta + o_cand); Q.ncand = (uint32_t)dcands.size();
           Q.has_bwt = has_bwt ? 1u : 0u; Q.max_raw = max_raw;
-          d.t_post.start(s);
-          if (want_native_post()) { CU(launch_post_native(Q, s)); launches += 4; }
-          else CU(cudaMemsetAsync(meta + o_kind, 0, 4ull * jobs.size(), s));
-          CU(launch_post(Q, s));
-          d.t_post.stop(s);
+          G.t_post.start(s);
+          if (want_native_post()) { CU(launch_post_native(Q, G.stream)); launches += 4; }
+          else CU(cudaMemsetAsync(meta + o_kind, 0, 4ull * jobs.size(), G.stream));
+          CU(launch_post(Q, G.stream));
+          G.t_post.stop(s);
           ++launches;
         }
         std::vector<BlockResult> r(jobs.size());
         std::vector<uint32_t> kinds(jobs.size());
         std::vector<uint64_t> sout(nseg, 0);
-        CU(cudaMemcpyAsync(sout.data(), meta + o_sout, 8ull * nseg, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(r.data(), meta + o_res, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(kinds.data(), meta + o_kind, 4ull * jobs.size(), cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        CU(cudaMemcpyAsync(sout.data(), meta + o_sout, 8ull * nseg, cudaMemcpyDeviceToHost, G.stream));
+        CU(cudaMemcpyAsync(r.data(), meta + o_res, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, G.stream));
+        CU(cudaMemcpyAsync(kinds.data(), meta + o_kind, 4ull * jobs.size(), cudaMemcpyDeviceToHost, G.stream));
+        CU(cudaStreamSynchronize(G.stream));
+        std::lock_guard<std::mutex> res_lk(res_mu);
         for (uint32_t kd : kinds) { if ((kd & 15u) == PK_GENERIC) ++post_interp; else ++post_native; }
-        codec_ms += d.t_codec.ms();
-        post_ms += d.t_post.ms();
+        codec_ms += G.t_codec.ms();
+        post_ms += G.t_post.ms();
         d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
         snprintf(d.stats.kernel, sizeof d.stats.kernel, "%s", L.kernel.c_str());
         for (size_t k = 0; k < ids.size(); ++k) {
@@ -928,8 +949,39 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         // a header this build cannot run (or that does not fit) takes its own blocks down, not the batch
         if (f.code == ZPQ_E_CUDA) throw;
         cudaGetLastError();
+        std::lock_guard<std::mutex> res_lk(res_mu);
         for (uint32_t i : ids) { res[i - b0].status = ZPQ_BLOCK_CORRUPT; res[i - b0].out_len = 0; fail_block(i, ZPQ_BLOCK_CORRUPT, f.what()); }
       }
+    };
+    if (groups.size() <= 1) {
+      for (auto& g : groups) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post});
+    } else {
+      // several models in the batch: one host thread and one stream per group (a group is a handful of latency-bound kernels;
+      // run one after the other they would each wait for the longest chain of the one before)
+      while (d.pool.size() + 1 < groups.size()) { d.pool.emplace_back(new Scratch); d.pool.back()->init(); }
+      CU(cudaEventRecord(d.ev_ready, s));
+      std::vector<std::thread> th;
+      std::vector<std::string> terr(groups.size());
+      std::vector<int> tcode(groups.size(), 0);
+      size_t gi = 0;
+      for (auto& g : groups) {
+        const size_t k = gi++;
+        th.emplace_back([&, k]() {
+          try {
+            CU(cudaSetDevice(d.id));
+            if (k == 0) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post});
+            else {
+              Scratch& sc = *d.pool[k - 1];
+              CU(cudaStreamWaitEvent(sc.stream, d.ev_ready, 0));
+              run_group(g.second, GroupBufs{sc.work, sc.meta, sc.plan, sc.arena, sc.stream, sc.t_codec, sc.t_post});
+            }
+          } catch (const Failure& f) { tcode[k] = f.code; terr[k] = f.what(); }
+          catch (const std::exception& e) { tcode[k] = ZPQ_E_CUDA; terr[k] = e.what(); }
+        });
+      }
+      for (auto& t : th) t.join();
+      for (auto& sc : d.pool) sc->release();                     // the next call may need all of HBM for one model
+      for (size_t k = 0; k < groups.size(); ++k) if (tcode[k]) throw Failure(tcode[k], terr[k]);
     }
     std::vector<uint32_t> again;
     for (uint32_t i : pending)
