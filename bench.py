@@ -701,7 +701,7 @@ def main():
     configs = {}
     if not args.no_configs:
         for cid in ("C1", "C2a", "C2b", "C2c", "C3", "C4"):
-            if cid == head_id:
+            if cid == head_id or args.config == "C5":       # --config C5: the headline line plus the FULL sweep, nothing else
                 continue
             try:
                 rig.close(); rig.open()                 # the library's buffers are grow-only: every config starts from an empty device
