@@ -840,7 +840,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
     std::map<Bytes, std::vector<uint32_t>> groups;
     for (uint32_t i : pending) groups[blocks[i].ref.hdr.wire].push_back(i);
     std::mutex alloc_mu, res_mu;
-    auto run_group = [&](const std::vector<uint32_t>& ids, GroupBufs G) {
+    auto run_group = [&](const std::vector<uint32_t>& ids, GroupBufs G, bool may_defer) {
       const Header& hdr = blocks[ids[0]].ref.hdr;
       try {
         std::vector<DecJob> jobs(ids.size());
@@ -948,17 +948,20 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
       } catch (const Failure& f) {
         // a header this build cannot run (or that does not fit) takes its own blocks down, not the batch
         if (f.code == ZPQ_E_CUDA) throw;
+        if (f.code == ZPQ_E_NOMEM && may_defer) throw;          // no room beside the other groups: it runs alone afterwards
         cudaGetLastError();
         std::lock_guard<std::mutex> res_lk(res_mu);
         for (uint32_t i : ids) { res[i - b0].status = ZPQ_BLOCK_CORRUPT; res[i - b0].out_len = 0; fail_block(i, ZPQ_BLOCK_CORRUPT, f.what()); }
       }
     };
     if (groups.size() <= 1) {
-      for (auto& g : groups) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post});
+      for (auto& g : groups) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, false);
     } else {
       // several models in the batch: one host thread and one stream per group (a group is a handful of latency-bound kernels;
       // run one after the other they would each wait for the longest chain of the one before)
       while (d.pool.size() + 1 < groups.size()) { d.pool.emplace_back(new Scratch); d.pool.back()->init(); }
+      CU(cudaStreamSynchronize(s));
+      d.arena.release();                                         // what an earlier call left there: every group takes what it needs
       CU(cudaEventRecord(d.ev_ready, s));
       std::vector<std::thread> th;
       std::vector<std::string> terr(groups.size());
@@ -969,11 +972,11 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         th.emplace_back([&, k]() {
           try {
             CU(cudaSetDevice(d.id));
-            if (k == 0) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post});
+            if (k == 0) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, true);
             else {
               Scratch& sc = *d.pool[k - 1];
               CU(cudaStreamWaitEvent(sc.stream, d.ev_ready, 0));
-              run_group(g.second, GroupBufs{sc.work, sc.meta, sc.plan, sc.arena, sc.stream, sc.t_codec, sc.t_post});
+              run_group(g.second, GroupBufs{sc.work, sc.meta, sc.plan, sc.arena, sc.stream, sc.t_codec, sc.t_post}, true);
             }
           } catch (const Failure& f) { tcode[k] = f.code; terr[k] = f.what(); }
           catch (const std::exception& e) { tcode[k] = ZPQ_E_CUDA; terr[k] = e.what(); }
@@ -981,7 +984,13 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
       }
       for (auto& t : th) t.join();
       for (auto& sc : d.pool) sc->release();                     // the next call may need all of HBM for one model
-      for (size_t k = 0; k < groups.size(); ++k) if (tcode[k]) throw Failure(tcode[k], terr[k]);
+      for (size_t k = 0; k < groups.size(); ++k) if (tcode[k] && tcode[k] != ZPQ_E_NOMEM) throw Failure(tcode[k], terr[k]);
+      gi = 0;
+      for (auto& g : groups) {                                   // groups that found no room beside the others: one at a time
+        if (tcode[gi++] != ZPQ_E_NOMEM) continue;
+        cudaGetLastError();
+        run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, false);
+      }
     }
     std::vector<uint32_t> again;
     for (uint32_t i : pending)

@@ -104,21 +104,21 @@ __global__ void __launch_bounds__(256) k_post_pass(const PostParams Q) {
     for (uint32_t k = 0; k < J.seg_count; ++k) Q.seg_out_end[J.seg_first + k] = Q.seg_end[J.seg_first + k] - 1;
   }
   if (n > O.out_cap) return;
-  const uint64_t begin = (uint64_t)blockIdx.y * kPassChunk;
-  if (begin >= n) return;
-  const uint64_t end = min(n, begin + kPassChunk);
   const uint8_t* src = Q.raw + J.out_off + 1;
   uint8_t* dst = Q.out + O.out_off;
-  // slots are 16-byte aligned and the chunk size is a multiple of 4: whole words from two aligned source words
-  if (((uintptr_t)dst & 3u) == 0) {
-    const uint32_t sh = (uint32_t)((uintptr_t)(src + begin) & 3u) * 8u;
-    const uint32_t* s32 = reinterpret_cast<const uint32_t*>((uintptr_t)(src + begin) & ~(uintptr_t)3);
-    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + begin);
-    const uint64_t words = (end - begin) / 4;
-    for (uint64_t i = threadIdx.x; i < words; i += blockDim.x) d32[i] = __funnelshift_r(s32[i], s32[i + 1], sh);
-    for (uint64_t i = begin + words * 4 + threadIdx.x; i < end; i += blockDim.x) dst[i] = src[i];
-  } else {
-    for (uint64_t i = begin + threadIdx.x; i < end; i += blockDim.x) dst[i] = src[i];
+  for (uint64_t begin = (uint64_t)blockIdx.y * kPassChunk; begin < n; begin += (uint64_t)gridDim.y * kPassChunk) {
+    const uint64_t end = min(n, begin + kPassChunk);
+    // slots are 16-byte aligned and the chunk size is a multiple of 4: whole words from two aligned source words
+    if (((uintptr_t)dst & 3u) == 0) {
+      const uint32_t sh = (uint32_t)((uintptr_t)(src + begin) & 3u) * 8u;
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>((uintptr_t)(src + begin) & ~(uintptr_t)3);
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + begin);
+      const uint64_t words = (end - begin) / 4;
+      for (uint64_t i = threadIdx.x; i < words; i += blockDim.x) d32[i] = __funnelshift_r(s32[i], s32[i + 1], sh);
+      for (uint64_t i = begin + words * 4 + threadIdx.x; i < end; i += blockDim.x) dst[i] = src[i];
+    } else {
+      for (uint64_t i = begin + threadIdx.x; i < end; i += blockDim.x) dst[i] = src[i];
+    }
   }
 }
 
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kBwtThreads) k_post_bwt(const PostParams Q) {
 cudaError_t launch_post_native(const PostParams& q, cudaStream_t s) {
   if (!q.njobs) return cudaSuccess;
   k_post_classify<<<(q.njobs + 7) / 8, 256, 0, s>>>(q);
-  const uint32_t chunks = (uint32_t)std::max<uint64_t>(1, (q.max_raw + kPassChunk - 1) / kPassChunk);
+  const uint32_t chunks = (uint32_t)std::min<uint64_t>(65535, std::max<uint64_t>(1, (q.max_raw + kPassChunk - 1) / kPassChunk));
   k_post_pass<<<dim3(q.njobs, chunks), 256, 0, s>>>(q);
   if (q.ncand) {
     k_post_lz<<<(q.njobs + 3) / 4, 128, 0, s>>>(q);

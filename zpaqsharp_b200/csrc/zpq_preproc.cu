@@ -462,32 +462,33 @@ __global__ void __launch_bounds__(256) k_gap_hist(const uint8_t* in, const uint6
   __shared__ int hist[kGapBinsDev];
   const uint32_t b = blockIdx.x;
   const uint64_t n = off[b + 1] - off[b];
-  const uint64_t c0 = (uint64_t)blockIdx.y * kGapBinsDev;
-  if (c0 >= n) return;
   const uint8_t* p = in + (off[b] - off[0]);
-  const uint64_t lo = c0 >= (uint64_t)kGapBinsDev ? c0 - kGapBinsDev : 0;       // first byte held
-  const uint64_t hi = min(n, c0 + kGapBinsDev);
-  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) buf[i - lo] = p[i];
-  for (int k = threadIdx.x; k < kGapBinsDev; k += blockDim.x) hist[k] = 0;
-  __syncthreads();
-  for (uint64_t i = c0 + threadIdx.x; i < hi; i += blockDim.x) {
-    const uint32_t at = (uint32_t)(i - lo);
-    const uint8_t v = buf[at];
-    const uint32_t reach = (uint32_t)min((uint64_t)(kGapBinsDev - 1), i);      // gaps 1 .. reach can be seen
-    uint32_t k = 1;
-    while (k <= reach && buf[at - k] != v) ++k;
-    if (k <= reach) atomicAdd(&hist[k], 1);
-    else if (i > 0 && i < (uint64_t)kGapBinsDev) atomicAdd(&hist[(uint32_t)i], 1);   // never seen: "last seen at 0"
+  for (uint64_t c0 = (uint64_t)blockIdx.y * kGapBinsDev; c0 < n; c0 += (uint64_t)gridDim.y * kGapBinsDev) {
+    const uint64_t lo = c0 >= (uint64_t)kGapBinsDev ? c0 - kGapBinsDev : 0;       // first byte held
+    const uint64_t hi = min(n, c0 + kGapBinsDev);
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) buf[i - lo] = p[i];
+    for (int k = threadIdx.x; k < kGapBinsDev; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    for (uint64_t i = c0 + threadIdx.x; i < hi; i += blockDim.x) {
+      const uint32_t at = (uint32_t)(i - lo);
+      const uint8_t v = buf[at];
+      const uint32_t reach = (uint32_t)min((uint64_t)(kGapBinsDev - 1), i);      // gaps 1 .. reach can be seen
+      uint32_t k = 1;
+      while (k <= reach && buf[at - k] != v) ++k;
+      if (k <= reach) atomicAdd(&hist[k], 1);
+      else if (i > 0 && i < (uint64_t)kGapBinsDev) atomicAdd(&hist[(uint32_t)i], 1);   // never seen: "last seen at 0"
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kGapBinsDev; k += blockDim.x)
+      if (hist[k]) atomicAdd(&gap[(uint64_t)b * kGapBinsDev + k], hist[k]);
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < kGapBinsDev; k += blockDim.x)
-    if (hist[k]) atomicAdd(&gap[(uint64_t)b * kGapBinsDev + k], hist[k]);
 }
 cudaError_t launch_gap_hist(const uint8_t* in, const uint64_t* d_off, uint32_t nb, uint64_t max_len, int* gap, cudaStream_t s) {
   if (!nb) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(gap, 0, (size_t)nb * kGapBinsDev * sizeof(int), s);
   if (e != cudaSuccess) return e;
-  const uint32_t chunks = (uint32_t)((max_len + kGapBinsDev - 1) / kGapBinsDev);
+  const uint32_t chunks = (uint32_t)std::min<uint64_t>(65535, (max_len + kGapBinsDev - 1) / kGapBinsDev);
   if (!chunks) return cudaSuccess;
   k_gap_hist<<<dim3(nb, chunks), 256, 0, s>>>(in, d_off, gap);
   return cudaGetLastError();
