@@ -100,6 +100,13 @@ struct Scratch {
   void release() { work.release(); meta.release(); plan.release(); arena.release(); }
   void fini() { release(); t_codec.fini(); t_post.fini(); if (stream) cudaStreamDestroy(stream); stream = nullptr; }
 };
+// Every group of a multi-model batch takes its memory before any of them launches: cudaMalloc / cudaFree wait for running kernels,
+// so an allocation behind a launch would put the groups back in a row.
+struct GroupBarrier {
+  std::mutex m; std::condition_variable cv; size_t need = 0, got = 0;
+  void arrive() { std::lock_guard<std::mutex> lk(m); ++got; cv.notify_all(); }
+  void arrive_and_wait() { std::unique_lock<std::mutex> lk(m); ++got; cv.notify_all(); cv.wait(lk, [&] { return got >= need; }); }
+};
 struct GroupBufs { DevBuf& work; DevBuf& meta; DevBuf& plan; DevBuf& arena; cudaStream_t stream; Timer& t_codec; Timer& t_post; };
 
 struct Device {
@@ -840,8 +847,9 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
     std::map<Bytes, std::vector<uint32_t>> groups;
     for (uint32_t i : pending) groups[blocks[i].ref.hdr.wire].push_back(i);
     std::mutex alloc_mu, res_mu;
-    auto run_group = [&](const std::vector<uint32_t>& ids, GroupBufs G, bool may_defer) {
+    auto run_group = [&](const std::vector<uint32_t>& ids, GroupBufs G, bool may_defer, GroupBarrier* bar) {
       const Header& hdr = blocks[ids[0]].ref.hdr;
+      bool arrived = false;
       try {
         std::vector<DecJob> jobs(ids.size());
         std::vector<PostJob> pjobs(ids.size());
@@ -889,6 +897,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         G.arena.reserve((uint64_t)L.resident * L.plan->arena_bytes);
         G.plan.reserve(sizeof(Plan));
         alloc_lk.unlock();
+        if (bar) { arrived = true; bar->arrive_and_wait(); }
         CU(cudaMemcpyAsync(G.plan.p, L.plan.get(), sizeof(Plan) - sizeof(L.plan->hcomp) + L.plan->hcomp_len + 8,
                            cudaMemcpyHostToDevice, G.stream));
         CU(cudaMemcpyAsync(meta + o_jobs, jobs.data(), sizeof(DecJob) * jobs.size(), cudaMemcpyHostToDevice, G.stream));
@@ -946,23 +955,34 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
           seg_out[ids[k] - b0].assign(sout.begin() + jobs[k].seg_first, sout.begin() + jobs[k].seg_first + jobs[k].seg_count);
         }
       } catch (const Failure& f) {
+        if (bar && !arrived) { arrived = true; bar->arrive(); }
         // a header this build cannot run (or that does not fit) takes its own blocks down, not the batch
         if (f.code == ZPQ_E_CUDA) throw;
         if (f.code == ZPQ_E_NOMEM && may_defer) throw;          // no room beside the other groups: it runs alone afterwards
         cudaGetLastError();
         std::lock_guard<std::mutex> res_lk(res_mu);
         for (uint32_t i : ids) { res[i - b0].status = ZPQ_BLOCK_CORRUPT; res[i - b0].out_len = 0; fail_block(i, ZPQ_BLOCK_CORRUPT, f.what()); }
+      } catch (...) {
+        if (bar && !arrived) bar->arrive();
+        throw;
       }
     };
-    if (groups.size() <= 1) {
-      for (auto& g : groups) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, false);
+    // Side by side only when the groups together leave SMs free: a batch with thousands of blocks fills every SM with the first
+    // group's CTAs anyway, and the CTAs of the other groups queued between them only lengthen the tail (measured on the C5
+    // archives: 1024 blocks of 1 MB 121 -> 176 MB/s, 256 blocks of 4 MB 33 -> 66 MB/s, but 4096 blocks of 256 kB 395 -> 280 MB/s).
+    const bool side_by_side = groups.size() > 1 && pending.size() <= (size_t)d.sms * 8;
+    if (!side_by_side) {
+      for (auto& sc : d.pool) sc->release();                     // (a one-model batch may need all of HBM)
+      for (auto& g : groups) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, false, nullptr);
     } else {
       // several models in the batch: one host thread and one stream per group (a group is a handful of latency-bound kernels;
       // run one after the other they would each wait for the longest chain of the one before)
       while (d.pool.size() + 1 < groups.size()) { d.pool.emplace_back(new Scratch); d.pool.back()->init(); }
       CU(cudaStreamSynchronize(s));
-      d.arena.release();                                         // what an earlier call left there: every group takes what it needs
+      if (free_device_memory() < (16ull << 30)) d.arena.release();   // an earlier one-model call left all of HBM there
       CU(cudaEventRecord(d.ev_ready, s));
+      GroupBarrier bar;
+      bar.need = groups.size();
       std::vector<std::thread> th;
       std::vector<std::string> terr(groups.size());
       std::vector<int> tcode(groups.size(), 0);
@@ -970,26 +990,28 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
       for (auto& g : groups) {
         const size_t k = gi++;
         th.emplace_back([&, k]() {
+          bool entered = false;                                  // run_group always reaches the barrier once entered
           try {
             CU(cudaSetDevice(d.id));
-            if (k == 0) run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, true);
+            if (k == 0) { entered = true; run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, true, &bar); }
             else {
               Scratch& sc = *d.pool[k - 1];
               CU(cudaStreamWaitEvent(sc.stream, d.ev_ready, 0));
-              run_group(g.second, GroupBufs{sc.work, sc.meta, sc.plan, sc.arena, sc.stream, sc.t_codec, sc.t_post}, true);
+              entered = true;
+              run_group(g.second, GroupBufs{sc.work, sc.meta, sc.plan, sc.arena, sc.stream, sc.t_codec, sc.t_post}, true, &bar);
             }
-          } catch (const Failure& f) { tcode[k] = f.code; terr[k] = f.what(); }
-          catch (const std::exception& e) { tcode[k] = ZPQ_E_CUDA; terr[k] = e.what(); }
+          } catch (const Failure& f) { tcode[k] = f.code; terr[k] = f.what(); if (!entered) bar.arrive(); }
+          catch (const std::exception& e) { tcode[k] = ZPQ_E_CUDA; terr[k] = e.what(); if (!entered) bar.arrive(); }
         });
       }
       for (auto& t : th) t.join();
-      for (auto& sc : d.pool) sc->release();                     // the next call may need all of HBM for one model
       for (size_t k = 0; k < groups.size(); ++k) if (tcode[k] && tcode[k] != ZPQ_E_NOMEM) throw Failure(tcode[k], terr[k]);
       gi = 0;
       for (auto& g : groups) {                                   // groups that found no room beside the others: one at a time
         if (tcode[gi++] != ZPQ_E_NOMEM) continue;
         cudaGetLastError();
-        run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, false);
+        for (auto& sc : d.pool) sc->release();
+        run_group(g.second, GroupBufs{d.work, d.meta, d.plan, d.arena, s, d.t_codec, d.t_post}, false, nullptr);
       }
     }
     std::vector<uint32_t> again;

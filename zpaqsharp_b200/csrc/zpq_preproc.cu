@@ -295,46 +295,80 @@ __global__ void __launch_bounds__(128) k_lz77(const LzParams P) {
       // the reference rebuilds its windowed ISA when the entry of i is stale (LZBuffer.cs:256-259)
       if (built < 0) { if (sa[0] != i) built = i & wmask; }
       else if ((int64_t)(i & wmask) != built) built = i & wmask;
-      for (uint32_t h = 0; h <= lookahead; ++h) {
+      // one neighbour of rank q in direction dir at distance k, seen from look-ahead position h (LZBuffer.cs:262-272)
+      auto cand = [&](uint32_t h, uint32_t q, int dir, uint32_t k, bool on, uint32_t& p, uint32_t& l, uint32_t& l1) -> bool {
+        p = l = l1 = 0;
+        const int64_t at = (int64_t)q + (int64_t)dir * (int64_t)k;
+        if (!on || k > bucket || at < 0 || at >= (int64_t)n) return false;
+        p = sa[at] - h;                                  // unsigned wrap as in the reference when sa < h
+        if (!(p < i)) return false;
+        l = lz_match_fwd(in, n, p, i, h, maxMatch);
+        for (l1 = h; l1 > 0 && in[p + l1 - 1] == in[i + l1 - 1]; --l1) {}
+        return true;
+      };
+      // the reference's sequential scoring and early exit over the candidates of lanes [l0, l0 + cnt), in neighbour order
+      // (LZBuffer.cs:273-280); candidates that do not lie in front of i are passed over.  True: the reference stops here.
+      auto replay = [&](bool valid, uint32_t p, uint32_t l, uint32_t l1, uint32_t h, int l0, int cnt) -> bool {
+        uint32_t vm = __ballot_sync(FULL, valid);
+        vm &= cnt >= 32 ? 0xFFFFFFFFu : (((1u << cnt) - 1u) << l0);
+        while (vm) {
+          const int tl = __ffs((int)vm) - 1;
+          vm &= vm - 1;
+          const uint32_t cp = __shfl_sync(FULL, p, tl), cl = __shfl_sync(FULL, l, tl), cl1 = __shfl_sync(FULL, l1, tl);
+          int score = (int)(cl - cl1) * 8 - lg32(i - cp) - 4 * (lit == 0 && cl1 > 0) - 11;
+          for (uint32_t a = 0; a < h; ++a) score = score * 5 / 8;
+          if (score > bscore) { blen = cl; bp = cp; blit = cl1; bscore = score; }
+          if (cl < blen || cl < minMatch || cl > 255) return true;
+        }
+        return false;
+      };
+      // entry of t = h + i in the windowed ISA: valid only inside the built window (or the zero-filled initial array, which
+      // maps everything to rank 0); does not depend on what the search has found so far
+      auto entry = [&](uint32_t h, uint32_t& q) -> bool {
         const uint32_t t = h + i;
-        // entry of t in the windowed ISA: valid only inside the built window (or the zero-filled
-        // initial array, which maps everything to rank 0)
-        uint32_t q;
-        if (built < 0) { q = 0; if (sa[0] != t) continue; }
-        else {
-          if (t >= n || (int64_t)(t & wmask) != built) continue;
-          q = isa[t];
-        }
-        for (int dir = -1; dir <= 1; dir += 2) {
-          for (uint32_t k0 = 1; k0 <= bucket; k0 += 32) {
-            // 32 neighbours at a time: every lane measures one candidate
-            const uint32_t k = k0 + lane;
-            const int64_t at = (int64_t)q + (int64_t)dir * (int64_t)k;
-            uint32_t p = 0, l = 0, l1 = 0;
-            bool valid = false;
-            if (k <= bucket && at >= 0 && at < (int64_t)n) {
-              p = sa[at] - h;                       // unsigned wrap as in the reference when sa < h
-              if (p < i) {
-                valid = true;
-                l = lz_match_fwd(in, n, p, i, h, maxMatch);
-                for (l1 = h; l1 > 0 && in[p + l1 - 1] == in[i + l1 - 1]; --l1) {}
-              }
+        if (built < 0) { q = 0; return sa[0] == t; }
+        if (t >= n || (int64_t)(t & wmask) != built) return false;
+        q = isa[t];
+        return true;
+      };
+      if (lookahead <= 1 && bucket >= 16) {
+        // Usually the reference stops within a few neighbours (the first one in front of i that matches worse than the best so
+        // far ends a direction).  So the nearest neighbours of EVERY (look-ahead position, direction) pair are measured in one
+        // warp round -- 32 / pairs lanes each -- and the pairs are replayed in the reference's order; a direction that is not
+        // finished by then goes on 32 neighbours at a time.
+        const uint32_t npair = 2 * (lookahead + 1), gsz = 32 / npair;
+        uint32_t hq[2] = {0, 0};
+        bool hon[2] = {false, false};
+        for (uint32_t h = 0; h <= lookahead; ++h) hon[h] = entry(h, hq[h]);
+        const uint32_t c = (uint32_t)lane / gsz, hc = c >> 1;
+        uint32_t p, l, l1;
+        const bool valid = cand(hc, hq[hc], (c & 1) ? 1 : -1, (uint32_t)lane % gsz + 1, hon[hc], p, l, l1);
+        for (uint32_t h = 0; h <= lookahead; ++h) {
+          if (!hon[h]) continue;
+          for (uint32_t dd = 0; dd < 2; ++dd) {
+            bool brk = replay(valid, p, l, l1, h, (int)((2 * h + dd) * gsz), (int)gsz);
+            for (uint32_t k0 = gsz + 1; !brk && k0 <= bucket; k0 += 32) {
+              uint32_t p2, l2, l12;
+              const bool v2 = cand(h, hq[h], dd ? 1 : -1, k0 + (uint32_t)lane, true, p2, l2, l12);
+              brk = replay(v2, p2, l2, l12, h, 0, 32);
             }
-            // apply the reference's sequential scoring and early exit in neighbour order
-            bool brk = false;
-            for (int tl = 0; tl < 32 && k0 + tl <= bucket; ++tl) {
-              const bool v = __shfl_sync(FULL, valid, tl);
-              if (!v) continue;
-              const uint32_t cp = __shfl_sync(FULL, p, tl), cl = __shfl_sync(FULL, l, tl), cl1 = __shfl_sync(FULL, l1, tl);
-              int score = (int)(cl - cl1) * 8 - lg32(i - cp) - 4 * (lit == 0 && cl1 > 0) - 11;
-              for (uint32_t a = 0; a < h; ++a) score = score * 5 / 8;
-              if (score > bscore) { blen = cl; bp = cp; blit = cl1; bscore = score; }
-              if (cl < blen || cl < minMatch || cl > 255) { brk = true; break; }
-            }
-            if (brk) break;
           }
+          if (bscore <= 0 || blen < minMatch) break;
         }
-        if (bscore <= 0 || blen < minMatch) break;
+      } else {
+        for (uint32_t h = 0; h <= lookahead; ++h) {
+          uint32_t q;
+          if (!entry(h, q)) continue;
+          for (int dir = -1; dir <= 1; dir += 2) {
+            for (uint32_t k0 = 1; k0 <= bucket; k0 += 32) {
+              // 32 neighbours at a time: every lane measures one candidate
+              uint32_t p, l, l1;
+              const bool valid = cand(h, q, dir, k0 + (uint32_t)lane, true, p, l, l1);
+              if (replay(valid, p, l, l1, h, 0, 32)) break;
+            }
+          }
+          if (bscore <= 0 || blen < minMatch) break;
+        }
       }
       const uint32_t offv = i - bp;
       if (offv > 0 && bscore > 0 && blen - blit >= minMatch + (P.level == 2) * ((offv >= (1u << 16)) + (offv >= (1u << 24)))) {

@@ -253,7 +253,10 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            load().zpq_destroy(self._h)
+            try:
+                load().zpq_destroy(self._h)
+            except TypeError:              # interpreter shutdown: the module globals are gone, the process frees the device
+                pass
             self._h = None
 
     __del__ = close
