@@ -264,7 +264,15 @@ __device__ __forceinline__ uint32_t lz_byte(const uint8_t* in, uint32_t n, uint3
 // length of the common prefix of in[p+from..] and in[i+from..], capped (forward match, LZBuffer.cs:264,298,318)
 __device__ __forceinline__ uint32_t lz_match_fwd(const uint8_t* in, uint32_t n, uint32_t p, uint32_t i, uint32_t from, uint32_t maxMatch) {
   uint32_t l = from;
-  while (i + l < n && l < maxMatch && in[p + l] == in[i + l]) ++l;
+  // four byte pairs per step (eight independent loads in flight instead of two), then byte by byte up to the first difference
+  const uint32_t lim = min(maxMatch, n - i);                  // l stays below both i + l < n and l < maxMatch
+  while (l + 4 <= lim) {
+    const bool e0 = in[p + l] == in[i + l], e1 = in[p + l + 1] == in[i + l + 1], e2 = in[p + l + 2] == in[i + l + 2],
+               e3 = in[p + l + 3] == in[i + l + 3];
+    if (!(e0 && e1 && e2 && e3)) break;
+    l += 4;
+  }
+  while (l < lim && in[p + l] == in[i + l]) ++l;
   return l;
 }
 
