@@ -132,3 +132,26 @@ def test_role_split_encoder_plan_for_builtin_models(zlib_):
     hdr, _ = zlib_.compile_config(zlib_.make_config("x0,0" + "c0,0,255" * 40)[0], [0] * 9) if hasattr(zlib_, "compile_config") else (None, None)
     if hdr:
         assert zlib_.encoder_plan(hdr)["applies"] == 0
+
+
+def test_find_blocks_locates_segment_ends_at_every_alignment(zlib_, oracle):
+    """The host framing parse probes every fourth byte for the four zero bytes that end coded data (Decoder.skip, Decoder.cs:70-98);
+    archives shifted by 0..7 junk bytes, with short zero runs inside the coded data, must give the same block boundaries."""
+    from tools import synth
+    arcs = []
+    for i in range(12):
+        d = synth.blocks("mixed", 2000 + i, 1, 3000 + 37 * i).tobytes() + b"\x00" * (i % 5) + bytes(range(i))
+        arcs.append(oracle.compress_block_level(d, 1) if i % 3 else oracle.compress_block(d, "x0,0c0,0,255"))
+    for shift in range(8):
+        junk = bytes([7] * shift)
+        blob = junk + b"".join(arcs)
+        got = zlib_.find_blocks(blob)
+        want, pos = [], shift
+        for a in arcs:
+            want.append((pos + 13, pos + len(a)))            # the block starts at "zPQ", behind the 13-byte tag
+            pos += len(a)
+        assert got == want
+    # stored (n = 0) blocks: lengths, not zero runs, delimit the data
+    d = b"\x00" * 5000 + synth.blocks("text", 1, 1, 2000).tobytes()
+    a = oracle.compress_block(d, "0")
+    assert zlib_.find_blocks(a + a) == [(13, len(a)), (len(a) + 13, 2 * len(a))]
