@@ -389,12 +389,16 @@ __device__ __forceinline__ void fd_bit(const Shared& S, FdCtx<FD>& X, const FdLa
 
   // ---- hash rows of the second nibble, a nibble ahead (helper lanes: one candidate per lane group) ----
   if (FD::M_ICM | FD::M_ISSE) {
+#ifndef ZPQ_FDEC_NO_PF8
+    // one bit known: pull the 8 rows the second nibble can use into L2.  (Measured, profiles/README.md: worth 1 - 2 % of the
+    // kernel time at 12 blocks per SM -- 1110 .. 1125 ms with, 1138 ms without on 1776 x 200 kB -- for 2.35 kB of DRAM reads per
+    // input byte, 38 % of the kernel's traffic; -DZPQ_FDEC_NO_PF8 turns it off.)
     if (K == 0) {
-      // one bit known: pull the 8 rows the second nibble can use into L2
       const uint32_t cx = r.h + 16u * (c8new * 8u + grp * 2u);
       prefetch_l2(r.tab + ((cx * 16u) & r.mask));
       prefetch_l2(r.tab + (((cx + 16u) * 16u) & r.mask));
     }
+#endif
     if (K == 1) {
       fd_find_issue(r, r.h + 16u * (c8new * 4u + grp), X.f0, X.f1, X.f2, X.fh0, X.fchk);
       const uint32_t oat = __shfl_sync(ZPQ_FULL, X.at, (int)gl);
