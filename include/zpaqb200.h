@@ -183,7 +183,9 @@ typedef struct zpq_stats {
   char kernel[96];                             /* which coding kernel ran: "lanes/aot2 (HCOMP compiled)", "lanes/nvrtc", ... */
   double post_kernel_ms;                       /* decode: the post-processing pass (PostProcessor.cs:37-86) behind the decoding kernel */
   uint32_t post_native_blocks;                 /* decode: blocks restored by a native kernel (PASS copy, LZ77, BWT, E8E9) ... */
-  uint32_t post_interpreted_blocks;            /* ... and blocks whose stored PCOMP program was interpreted */
+  uint32_t post_interpreted_blocks;            /* ... blocks whose stored PCOMP program was interpreted ... */
+  uint32_t post_compiled_blocks;               /* ... and blocks whose stored program ran as NVRTC-compiled code */
+  uint32_t reserved0;
 } zpq_stats;
 int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out);
 
@@ -201,6 +203,13 @@ int64_t zpq_specialize_model(const uint8_t* hdr, uint64_t hdr_len, char* source,
  * byte-aligned LZ77 (:577-638; param = minMatch), 4 = "bwtrle" inverse BWT (:644-794), 5 = "e8e9" (:801-826); e8 = the
  * program ends with the inverse E8E9 pass.  The programs are recognised byte for byte against what makeConfig emits. */
 int64_t zpq_post_kind(int ph, int pm, const uint8_t* pcomp, uint64_t len);
+
+/* The device analogue of the reference's x86 JIT for PCOMP (ZPAQL.assemble, ZPAQL.cs:353-1008): translate a PCOMP program to
+ * CUDA and compile it with NVRTC for sm_100a, as the decoder does for stored programs that are not one of makeConfig's four
+ * (ZPQ_POST_NVRTC=0 leaves them to the interpreter).  Needs no GPU.  Returns the cubin size, or a negative error with the
+ * compiler log in `log`; `source` (may be NULL) receives the generated text. */
+int64_t zpq_specialize_pcomp(int ph, int pm, const uint8_t* pcomp, uint64_t len, char* source, uint64_t source_cap, char* log,
+                             uint64_t log_cap);
 
 /* Library / build identification: "zpaqb200 <version> sm_100a". */
 const char* zpq_version(void);

@@ -35,17 +35,26 @@ def _x86ish(n, seed):
 
 
 def _decode_both(ctx, arc, offs):
+    """Native kernels, then the stored program compiled with NVRTC (ZPQ_NATIVE_POST=0), then the stored program interpreted
+    (ZPQ_POST_NVRTC=0 as well): all three must restore the same bytes."""
     out, ooff, sha, bst = ctx.decompress_blocks(arc, offs)
     st = ctx.stats()
     os.environ["ZPQ_NATIVE_POST"] = "0"
     try:
         out2, ooff2, sha2, bst2 = ctx.decompress_blocks(arc, offs)
         st2 = ctx.stats()
+        os.environ["ZPQ_POST_NVRTC"] = "0"
+        out3, ooff3, sha3, bst3 = ctx.decompress_blocks(arc, offs)
+        st3 = ctx.stats()
     finally:
         os.environ.pop("ZPQ_NATIVE_POST", None)
-    assert out.tobytes() == out2.tobytes() and ooff.tolist() == ooff2.tolist()
-    assert sha.tolist() == sha2.tolist() and bst.tolist() == bst2.tolist()
-    assert st2.post_native_blocks == 0
+        os.environ.pop("ZPQ_POST_NVRTC", None)
+    assert out.tobytes() == out2.tobytes() == out3.tobytes() and ooff.tolist() == ooff2.tolist() == ooff3.tolist()
+    assert sha.tolist() == sha2.tolist() == sha3.tolist() and bst.tolist() == bst2.tolist() == bst3.tolist()
+    assert st2.post_native_blocks == st3.post_native_blocks and st3.post_compiled_blocks == 0
+    # without the native kernels every block that carries a program runs it as compiled code (PASS blocks are copied either way)
+    assert st2.post_compiled_blocks + st2.post_native_blocks + st2.post_interpreted_blocks == len(offs) - 1
+    assert st2.post_compiled_blocks >= st3.post_interpreted_blocks - st2.post_interpreted_blocks
     return out, ooff, sha, st
 
 
@@ -113,7 +122,7 @@ def test_damaged_and_truncated_streams_follow_the_program(gpu_ctx, oracle, metho
     assert st.post_native_blocks >= 1
 
 
-def test_foreign_program_is_interpreted(gpu_ctx, oracle):
+def test_foreign_program_is_compiled_or_interpreted(gpu_ctx, oracle):
     """A PCOMP program no makeConfig emits (a foreign archive's; loops and a long jump): SURVEY 8f-1."""
     from oracle import frontend as fe
     cfg = ("comp 2 4 0 0 1 0 cm 16 255 hcomp c++ *c=a b=c a=0 hash *d=a halt "
@@ -126,4 +135,13 @@ def test_foreign_program_is_interpreted(gpu_ctx, oracle):
     out, ooff, sha, bst = gpu_ctx.decompress_blocks(a, np.asarray([0, len(a)], dtype=np.uint64))
     st = gpu_ctx.stats()
     assert out.tobytes() == want
-    assert st.post_native_blocks == 0 and st.post_interpreted_blocks == 1
+    # no native kernel knows this program: it is translated and compiled (NVRTC for sm_100a) ...
+    assert st.post_native_blocks == 0 and st.post_compiled_blocks == 1 and st.post_interpreted_blocks == 0
+    # ... or, without NVRTC, interpreted
+    os.environ["ZPQ_POST_NVRTC"] = "0"
+    try:
+        out, ooff, sha, bst = gpu_ctx.decompress_blocks(a, np.asarray([0, len(a)], dtype=np.uint64))
+        st = gpu_ctx.stats()
+    finally:
+        os.environ.pop("ZPQ_POST_NVRTC", None)
+    assert out.tobytes() == want and st.post_compiled_blocks == 0 and st.post_interpreted_blocks == 1

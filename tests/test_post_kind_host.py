@@ -42,3 +42,27 @@ def test_other_programs_are_interpreted(zlib_):
     # a hand-written program (a foreign archive's): copies its input
     h2, p2 = zlib_.compile_config("comp 0 0 0 0 0 hcomp halt pcomp copy ; a> 255 ifnot out endif halt end", [0] * 9)
     assert zlib_.post_kind(0, 0, p2) == 0
+
+
+@pytest.mark.parametrize("method", ["x0,1,4,0,7,21,1", "x0,6,8,0,5,18c0,0,255", "x0,7ci1", "x5,7ci1", "x0,4c0,0,255"])
+def test_pcomp_programs_translate_and_compile_with_nvrtc(zlib_, method):
+    """The device analogue of the reference's x86 JIT for PCOMP (ZPAQL.cs:353-1008): ZPAQL -> CUDA -> sm_100a cubin, no GPU needed."""
+    text, args = zlib_.make_config(method)
+    hdr, pcomp = zlib_.compile_config(text, args)
+    n, src, log = zlib_.specialize_pcomp(hdr[4], hdr[5], pcomp)
+    assert n > 1000, log
+    assert "zpq_post_rt" in src and "zpq_prog_run" in src and "goto Lhalt;" in src
+
+
+def test_foreign_pcomp_with_loops_and_long_jumps_compiles(zlib_):
+    cfg = ("comp 2 4 0 0 1 0 cm 16 255 hcomp c++ *c=a b=c a=0 hash *d=a halt "
+           "pcomp foreign ; a> 255 ifnotl a^= 32 b=a c= 3 do a=b out c-- a=c a> 0 while elsel a= 33 out endif halt end")
+    hdr, pcomp = zlib_.compile_config(cfg, [0] * 9)
+    assert 255 in pcomp                                           # an LJ is in there
+    n, src, log = zlib_.specialize_pcomp(0, 0, pcomp)
+    assert n > 1000, log
+    assert "if (--budget == 0) goto Lerr;" in src                 # the backward jump of the loop is bounded
+    # a jump into the middle of an instruction cannot be translated: reported, left to the interpreter
+    bad = bytes([63, 0, 71, 5, 63, 0xFD, 56, 0])                   # jmp +0 ; a= 5 ; jmp -3 (into the operand of a=) ; halt
+    n, src, log = zlib_.specialize_pcomp(0, 0, bad)
+    assert n < 0 and "middle of an instruction" in log

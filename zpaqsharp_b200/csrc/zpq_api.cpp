@@ -31,6 +31,8 @@ namespace zpq {
 bool find_spec_kernels(const Header& hdr, uint32_t smem_limit, SpecKernels& out, std::string* why_not);
 void spec_set_smem_limit(uint32_t bytes);
 Bytes nvrtc_compile(const std::string& src);
+const void* find_post_kernel(const Bytes& prog, int ph, int pm, std::string* why_not);
+int64_t post_program_cubin(const Bytes& prog, int ph, int pm, std::string* source, std::string* log);
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
                                   const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g, bool* fdec);
 }
@@ -814,7 +816,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
   std::vector<std::vector<uint64_t>> seg_out(nbr);      // restored bytes of a block at the end of each of its segments
   std::atomic<uint32_t> launches{0};
   double codec_ms = 0, post_ms = 0;
-  uint32_t post_native = 0, post_interp = 0;
+  uint32_t post_native = 0, post_interp = 0, post_compiled = 0;
   d.t_kern.start(s);
   auto fail_block = [&](uint32_t i, uint8_t st, const std::string& why) {
     bstat[i] = st; R.any_corrupt = true;
@@ -933,6 +935,47 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
           G.t_post.start(s);
           if (want_native_post()) { CU(launch_post_native(Q, G.stream)); launches += 4; }
           else CU(cudaMemsetAsync(meta + o_kind, 0, 4ull * jobs.size(), G.stream));
+          // Blocks left over (foreign programs; streams a native kernel handed back): their stored program is translated to
+          // C and compiled with NVRTC for sm_100a -- one kernel per distinct program, at most four per batch -- and whatever
+          // that does not take is interpreted.
+          {
+            std::vector<uint32_t> kd(jobs.size());
+            std::vector<Bytes> tried;
+            for (int round = 0; round < 4; ++round) {
+              CU(cudaMemcpyAsync(kd.data(), meta + o_kind, 4ull * jobs.size(), cudaMemcpyDeviceToHost, G.stream));
+              CU(cudaStreamSynchronize(G.stream));
+              Bytes prog;
+              for (size_t k = 0; k < jobs.size() && prog.empty(); ++k) {
+                if ((kd[k] & 15u) != PK_GENERIC) continue;
+                uint8_t h3[3] = {0, 0, 0};
+                CU(cudaMemcpy(h3, G.work.as<uint8_t>() + jobs[k].out_off, 3, cudaMemcpyDeviceToHost));
+                const uint32_t psize = h3[1] + 256u * h3[2];
+                if (h3[0] != 1 || psize < 1 || 3ull + psize > jobs[k].out_cap) continue;
+                Bytes pg(psize);
+                CU(cudaMemcpy(pg.data(), G.work.as<uint8_t>() + jobs[k].out_off + 3, psize, cudaMemcpyDeviceToHost));
+                if (std::find(tried.begin(), tried.end(), pg) == tried.end()) prog.swap(pg);
+              }
+              if (prog.empty()) break;
+              tried.push_back(prog);
+              std::string why;
+              const void* kern = find_post_kernel(prog, hdr.ph, hdr.pm, &why);
+              if (!kern) continue;
+              const uint64_t o_prog = 0;
+              DevBuf pbuf;                                     // program bytes + job counter; lives until the sync below
+              pbuf.reserve(align_up(prog.size(), 256) + 256);
+              CU(cudaMemcpyAsync(pbuf.as<uint8_t>() + o_prog, prog.data(), prog.size(), cudaMemcpyHostToDevice, G.stream));
+              CU(cudaMemsetAsync(pbuf.as<uint8_t>() + align_up(prog.size(), 256), 0, 256, G.stream));
+              const uint8_t* d_prog = pbuf.as<uint8_t>();
+              uint32_t plen = (uint32_t)prog.size();
+              uint32_t* d_cnt = (uint32_t*)(pbuf.as<uint8_t>() + align_up(prog.size(), 256));
+              void* args[] = {&Q, &d_prog, &plen, &d_cnt};
+              const uint32_t warps = std::min<uint32_t>(Q.resident, Q.njobs);
+              CU(cudaLaunchKernel(kern, dim3((warps + 3) / 4), dim3(128), args, 0, G.stream));
+              ++launches;
+              CU(cudaStreamSynchronize(G.stream));
+              pbuf.release();
+            }
+          }
           CU(launch_post(Q, G.stream));
           G.t_post.stop(s);
           ++launches;
@@ -945,7 +988,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
         CU(cudaMemcpyAsync(kinds.data(), meta + o_kind, 4ull * jobs.size(), cudaMemcpyDeviceToHost, G.stream));
         CU(cudaStreamSynchronize(G.stream));
         std::lock_guard<std::mutex> res_lk(res_mu);
-        for (uint32_t kd : kinds) { if ((kd & 15u) == PK_GENERIC) ++post_interp; else ++post_native; }
+        for (uint32_t kd : kinds) { if ((kd & 15u) == PK_GENERIC) ++post_interp; else if ((kd & 15u) == PK_COMPILED) ++post_compiled; else ++post_native; }
         codec_ms += G.t_codec.ms();
         post_ms += G.t_post.ms();
         d.stats.resident_blocks = L.resident; d.stats.state_bytes_per_block = L.plan->arena_bytes;
@@ -1081,7 +1124,7 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
   }
   d.stats.kernel_ms = d.t_kern.ms(); d.stats.h2d_ms = d.t_h2d.ms();
   d.stats.codec_kernel_ms = codec_ms; d.stats.post_kernel_ms = post_ms; d.stats.launches = launches;
-  d.stats.post_native_blocks = post_native; d.stats.post_interpreted_blocks = post_interp;
+  d.stats.post_native_blocks = post_native; d.stats.post_interpreted_blocks = post_interp; d.stats.post_compiled_blocks = post_compiled;
 }
 
 void decompress_all(zpq_ctx* ctx, const uint8_t* in, const uint64_t* in_off, uint32_t nb, uint8_t* out, uint64_t out_cap,
@@ -1547,6 +1590,15 @@ int64_t zpq_post_kind(int ph, int pm, const uint8_t* pcomp, uint64_t len) {
     }
     return 0;
   } catch (const Failure& f) { return f.code; }
+}
+
+int64_t zpq_specialize_pcomp(int ph, int pm, const uint8_t* pcomp, uint64_t len, char* source, uint64_t source_cap, char* log, uint64_t log_cap) {
+  if (!pcomp || !len) return ZPQ_E_ARG;
+  std::string src, lg;
+  const int64_t n = post_program_cubin(Bytes(pcomp, pcomp + len), ph, pm, &src, &lg);
+  copy_out(src, source, source_cap);
+  copy_out(lg, log, log_cap);
+  return n;
 }
 
 int zpq_get_stats(zpq_ctx* ctx, zpq_stats* out) {

@@ -51,7 +51,7 @@ std::string store_stmt(int ddd, const std::string& e) {
 // Translate a ZPAQL program (incl. END byte) to the body of a C function.  Returns false when
 // the program cannot be compiled faithfully (jump into the middle of an instruction, undefined
 // opcode on a reachable path is still fine: it becomes `goto Lerr`).
-bool translate_zpaql(const uint8_t* code, int len, std::ostringstream& o) {
+bool translate_zpaql(const uint8_t* code, int len, std::ostringstream& o, bool with_out = false) {
   // linear sweep: instruction starts
   std::vector<int> start(len + 1, 0);
   std::vector<int> ilen(len + 1, 0);
@@ -90,7 +90,7 @@ bool translate_zpaql(const uint8_t* code, int len, std::ostringstream& o) {
       const int ddd = op >> 3, x = op & 7;
       if (ddd == 7) {
         if (x == 0) o << "goto Lhalt;";
-        else if (x == 1) o << "/* out: no destination in HCOMP */;";
+        else if (x == 1) { if (with_out) o << "{ if (opos < ocap) outp[opos] = (uint8_t)a; ++opos; }"; else o << "/* out: no destination in HCOMP */;"; }
         else if (x == 3) o << "a = (a + " << M_("b") << " + 512u) * 773u;";
         else if (x == 4) o << H_("d") << " = (" << H_("d") << " + a + 512u) * 773u;";
         else if (x == 7) o << jump(pc, pc + 2 + (((n + 128) & 255) - 128));
@@ -151,6 +151,94 @@ std::string lane_test(uint32_t mask) {
 
 // Source of one specialised model.  `name` becomes the model struct name; the kernels are
 // extern "C" <enc_kernel> / <dec_kernel>.
+// The post-processing pass for ONE PCOMP program, compiled: PostProcessor.write (PostProcessor.cs:37-86) with ZPAQL.run
+// (ZPAQL.cs:1028-1265) replaced by the program translated to straight C with gotos -- the device analogue of the reference's
+// x86 JIT for PCOMP (ZPAQL.cs:353-1008).  The kernel takes the jobs the native kernels left (jobkind == PK_GENERIC) whose stored
+// program is exactly `prog`, and marks them PK_COMPILED; everything else stays for the interpreter pass.  Returns "" when the
+// program cannot be translated faithfully.
+std::string generate_post_source(const Bytes& prog, int ph, int pm) {
+  std::ostringstream body;
+  if (prog.empty() || !translate_zpaql(prog.data(), (int)prog.size(), body, true)) return std::string();
+  std::ostringstream o;
+  o << "// generated by zpq_codegen.cpp: PCOMP program of " << prog.size() << " bytes, ph " << ph << ", pm " << pm << "\n"
+    << "#include \"zpq_plan.h\"\n"
+    << "namespace zpq {\n"
+    << "struct PVm { uint32_t b, c, d, f; };\n"
+    << "static __device__ __noinline__ int zpq_prog_run(uint32_t input, PVm& vm, uint32_t* const H, uint8_t* const M, uint32_t* const R,\n"
+    << "                                                uint8_t* const outp, uint64_t& opos_, const uint64_t ocap, long long budget) {\n"
+    << "  const uint32_t HMASK = " << ((1u << ph) - 1) << "u, MMASK = " << (uint32_t)((1ull << pm) - 1) << "u;\n"
+    << "  uint32_t a = input, b = vm.b, c = vm.c, d = vm.d, f = vm.f;\n"
+    << "  uint64_t opos = opos_;\n"
+    << "  int rc = 0;\n"
+    << "  (void)HMASK; (void)MMASK; (void)budget;\n"
+    << body.str()
+    << "  Lerr: rc = 1;\n"
+    << "  Lhalt:\n"
+    << "  vm.b = b; vm.c = c; vm.d = d; vm.f = f; opos_ = opos;\n"
+    << "  return rc;\n"
+    << "}\n"
+    << "}  // namespace zpq\n"
+    << R"ZPQK(
+extern "C" __global__ void __launch_bounds__(128) zpq_post_rt(const zpq::PostParams Q, const uint8_t* prog, uint32_t plen, uint32_t* counter) {
+  using namespace zpq;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= Q.resident) return;
+  const Plan* plan = Q.plan;
+  uint8_t* arena = Q.arenas + (uint64_t)gw * Q.arena_stride;
+  for (;;) {
+    uint32_t job = 0;
+    if (lane == 0) job = atomicAdd(counter, 1u);
+    job = __shfl_sync(0xFFFFFFFFu, job, 0);
+    if (job >= Q.njobs) break;
+    if ((Q.jobkind[job] & 15u) != PK_GENERIC) continue;
+    const DecJob J = Q.djobs[job];
+    const PostJob O = Q.pjobs[job];
+    const BlockResult R0 = Q.raw_results[job];
+    if (R0.status != 0 || !J.seg_count) continue;                    // the interpreter pass reports these
+    const uint8_t* raw = Q.raw + J.out_off;
+    const uint64_t* send = Q.seg_end + J.seg_first;
+    const uint64_t e0 = send[0];
+    if (e0 < 3 || raw[0] != 1) continue;
+    const uint32_t psize = raw[1] + 256u * raw[2];
+    if (psize != plen || 3ull + psize > e0) continue;
+    bool same = true;
+    for (uint32_t i = lane; i < psize; i += 32) same = same && raw[3 + i] == prog[i];
+    if (!__all_sync(0xFFFFFFFFu, same)) continue;
+    // ZPAQL.initp: H, M, R zeroed
+    uint32_t* H = reinterpret_cast<uint32_t*>(arena + plan->off_ph);
+    uint8_t* M = arena + plan->off_pm;
+    uint32_t* Rr = reinterpret_cast<uint32_t*>(arena + plan->off_pr);
+    const uint64_t hn = 1ull << plan->ph, mn4 = ((1ull << plan->pm) + 3) / 4;
+    for (uint64_t i = lane; i < hn; i += 32) H[i] = 0;
+    for (uint64_t i = lane; i < mn4; i += 32) reinterpret_cast<uint32_t*>(M)[i] = 0;
+    for (uint32_t i = lane; i < 256; i += 32) Rr[i] = 0;
+    __syncwarp();
+    uint32_t status = 0;
+    uint64_t opos = 0;
+    if (lane == 0) {
+      PVm vm; vm.b = vm.c = vm.d = vm.f = 0;
+      uint8_t* out = Q.out + O.out_off;
+      uint64_t pos = 3ull + psize;
+      for (uint32_t sg = 0; sg < J.seg_count && status == 0; ++sg) {
+        const uint64_t end = send[sg];
+        const long long budget = 65536 + 512 * (long long)(end + O.out_cap);
+        for (; pos < end; ++pos)
+          if (zpq_prog_run(raw[pos], vm, H, M, Rr, out, opos, O.out_cap, budget)) { status = 3; break; }       // ZPQ_BLOCK_ZPAQL
+        if (status == 0 && zpq_prog_run(0xFFFFFFFFu, vm, H, M, Rr, out, opos, O.out_cap, budget)) status = 3;
+        Q.seg_out_end[J.seg_first + sg] = opos;
+      }
+      if (status == 0 && opos > O.out_cap) status = 1;                                                          // ZPQ_BLOCK_OVERFLOW
+      Q.results[job].out_len = opos; Q.results[job].status = status;
+      Q.jobkind[job] = PK_COMPILED;
+    }
+    __syncwarp();
+  }
+}
+)ZPQK";
+  return o.str();
+}
+
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
                                   const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g, bool* fdec) {
   std::unique_ptr<Plan> plp(new Plan);

@@ -188,7 +188,8 @@ struct CodecParams {
 // PK_GENERIC = PostProcessor.write with the stored PCOMP program interpreted (any program); the others are native kernels
 // for the PASS type and for the four programs makeConfig emits (LibZPAQ.cs:427-826), recognised by comparing the stored
 // program with the host front end's own output for the block's (ph, pm).
-enum PostKind : uint32_t { PK_GENERIC = 0, PK_PASS = 1, PK_LZ_BITS = 2, PK_LZ_BYTES = 3, PK_BWT = 4, PK_E8E9 = 5 };
+enum PostKind : uint32_t { PK_GENERIC = 0, PK_PASS = 1, PK_LZ_BITS = 2, PK_LZ_BYTES = 3, PK_BWT = 4, PK_E8E9 = 5,
+                           PK_COMPILED = 6 /* restored by the stored program compiled with NVRTC (zpq_codegen.cpp: generate_post_source) */ };
 struct PostCand {             // one recognisable program
   uint32_t kind, e8, param;   // param: LZ_BITS rb (LibZPAQ.cs:427); LZ_BYTES: taken from the program byte at `wild` (minMatch, "$3")
   uint32_t off, len;          // program bytes at cand_bytes + off

@@ -19,6 +19,8 @@ namespace zpq {
 std::string generate_model_source(const Header& hdr, const std::string& name, const std::string& enc_kernel,
                                   const std::string& dec_kernel, bool* compiled_hcomp, int* duo_g, bool* fdec);
 
+std::string generate_post_source(const Bytes& prog, int ph, int pm);
+
 namespace {
 
 #include "gen/zpq_embed.inc"   // kEmbedPlan[], kEmbedDevcore[]: the headers NVRTC needs, as text
@@ -137,6 +139,50 @@ bool find_spec_kernels(const Header& hdr, uint32_t smem_limit, SpecKernels& out,
     if (why_not) *why_not = ex.what();
     return false;
   }
+}
+
+// The post-processing kernel compiled for one PCOMP program (zpq_codegen.cpp: generate_post_source), or null when the program
+// cannot be translated / NVRTC is not there (the interpreter pass then runs the program).  Cached per (program, ph, pm).
+const void* find_post_kernel(const Bytes& prog, int ph, int pm, std::string* why_not) {
+  static std::mutex mu;
+  static std::map<Bytes, const void*> table;          // null = known not to build
+  static std::map<Bytes, std::string> reason;
+  const char* e = getenv("ZPQ_POST_NVRTC");
+  if (e && *e == '0') { if (why_not) *why_not = "ZPQ_POST_NVRTC=0"; return nullptr; }
+  Bytes key = prog;
+  key.push_back((uint8_t)ph); key.push_back((uint8_t)pm);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = table.find(key);
+  if (it != table.end()) { if (!it->second && why_not) *why_not = reason[key]; return it->second; }
+  const void* k = nullptr;
+  try {
+    const std::string src = generate_post_source(prog, ph, pm);
+    if (src.empty()) throw Failure(ZPQ_E_UNSUPPORTED, "the program jumps into the middle of an instruction");
+    Bytes cubin = nvrtc_compile(src);
+    cudaLibrary_t lib = nullptr;
+    cudaError_t ce = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (ce != cudaSuccess) throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce));
+    cudaKernel_t kk = nullptr;
+    if ((ce = cudaLibraryGetKernel(&kk, lib, "zpq_post_rt")) != cudaSuccess)
+      throw Failure(ZPQ_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(ce));
+    k = (const void*)kk;
+  } catch (const std::exception& ex) {
+    cudaGetLastError();
+    reason[key] = ex.what();
+    if (why_not) *why_not = ex.what();
+  }
+  table[key] = k;
+  return k;
+}
+
+// NVRTC compile of a PCOMP program without loading it (needs no GPU): the cubin size, or a negative code with the log in *log.
+int64_t post_program_cubin(const Bytes& prog, int ph, int pm, std::string* source, std::string* log) {
+  try {
+    const std::string src = generate_post_source(prog, ph, pm);
+    if (source) *source = src;
+    if (src.empty()) { if (log) *log = "the program jumps into the middle of an instruction"; return ZPQ_E_UNSUPPORTED; }
+    return (int64_t)nvrtc_compile(src).size();
+  } catch (const Failure& f) { if (log) *log = f.what(); return f.code; }
 }
 
 // Ahead-of-time kernels need their dynamic shared memory limit raised once per device.

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "zpq_make_config", "zpq_expand_method", "zpq_compile_config", "zpq_builtin_model", "zpq_block_memory",
     "zpq_device_state_bytes", "zpq_device_state_bytes_for", "zpq_compress_blocks", "zpq_compress_blocks_level", "zpq_compress_blocks_model",
     "zpq_compress_blocks_model_dev", "zpq_find_blocks", "zpq_decompress_blocks", "zpq_decompressed_bound",
-    "zpq_get_stats", "zpq_version", "zpq_specialize_model", "zpq_encoder_plan", "zpq_post_kind",
+    "zpq_get_stats", "zpq_version", "zpq_specialize_model", "zpq_encoder_plan", "zpq_post_kind", "zpq_specialize_pcomp",
 ]
 
 
@@ -44,7 +44,8 @@ class Stats(C.Structure):
                 ("codec_kernel_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches", C.c_uint32), ("resident_blocks", C.c_uint32), ("state_bytes_per_block", C.c_uint64),
                 ("kernel", C.c_char * 96), ("post_kernel_ms", C.c_double),
-                ("post_native_blocks", C.c_uint32), ("post_interpreted_blocks", C.c_uint32)]
+                ("post_native_blocks", C.c_uint32), ("post_interpreted_blocks", C.c_uint32),
+                ("post_compiled_blocks", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 _lib = None
@@ -194,6 +195,17 @@ def post_kind(ph: int, pm: int, pcomp: bytes) -> int:
     L.zpq_post_kind.restype = C.c_int64
     L.zpq_post_kind.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint64]
     return int(L.zpq_post_kind(ph, pm, bytes(pcomp), len(pcomp)))
+
+
+def specialize_pcomp(ph: int, pm: int, pcomp: bytes):
+    """Translate + NVRTC-compile a PCOMP program -> (cubin size or error, source, log); needs no GPU."""
+    L = load()
+    L.zpq_specialize_pcomp.restype = C.c_int64
+    L.zpq_specialize_pcomp.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    src = C.create_string_buffer(1 << 20)
+    log = C.create_string_buffer(1 << 16)
+    n = L.zpq_specialize_pcomp(ph, pm, bytes(pcomp), len(pcomp), src, 1 << 20, log, 1 << 16)
+    return n, src.value.decode(), log.value.decode(errors="replace")
 
 
 def specialize_model(hdr: bytes):
