@@ -940,17 +940,19 @@ void decompress_range(zpq_ctx* ctx, Device& d, std::vector<DecBlock>& blocks, De
           // that does not take is interpreted.
           {
             std::vector<uint32_t> kd(jobs.size());
+            std::vector<BlockResult> rr(jobs.size());
             std::vector<Bytes> tried;
             for (int round = 0; round < 4; ++round) {
               CU(cudaMemcpyAsync(kd.data(), meta + o_kind, 4ull * jobs.size(), cudaMemcpyDeviceToHost, G.stream));
+              if (round == 0) CU(cudaMemcpyAsync(rr.data(), meta + o_raw, sizeof(BlockResult) * jobs.size(), cudaMemcpyDeviceToHost, G.stream));
               CU(cudaStreamSynchronize(G.stream));
               Bytes prog;
               for (size_t k = 0; k < jobs.size() && prog.empty(); ++k) {
-                if ((kd[k] & 15u) != PK_GENERIC) continue;
+                if ((kd[k] & 15u) != PK_GENERIC || rr[k].status != ZPQ_BLOCK_OK || rr[k].out_len < 4) continue;   // (damaged blocks: the interpreter pass reports them)
                 uint8_t h3[3] = {0, 0, 0};
                 CU(cudaMemcpy(h3, G.work.as<uint8_t>() + jobs[k].out_off, 3, cudaMemcpyDeviceToHost));
                 const uint32_t psize = h3[1] + 256u * h3[2];
-                if (h3[0] != 1 || psize < 1 || 3ull + psize > jobs[k].out_cap) continue;
+                if (h3[0] != 1 || psize < 1 || 3ull + psize > rr[k].out_len || psize > 8192) continue;              // (huge programs are not worth a compile)
                 Bytes pg(psize);
                 CU(cudaMemcpy(pg.data(), G.work.as<uint8_t>() + jobs[k].out_off + 3, psize, cudaMemcpyDeviceToHost));
                 if (std::find(tried.begin(), tried.end(), pg) == tried.end()) prog.swap(pg);
