@@ -659,6 +659,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the summary of the other configs (C1, C2b, C2c, C3, C4, C5)")
     ap.add_argument("--no-library-multi-gpu", action="store_true")
+    ap.add_argument("--all-configs", action="store_true", help="N > 1: also run the C1 .. C4 summary on every rank")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -703,6 +704,8 @@ def main():
         for cid in ("C1", "C2a", "C2b", "C2c", "C3", "C4"):
             if cid == head_id or args.config == "C5":       # --config C5: the headline line plus the FULL sweep, nothing else
                 continue
+            if world > 1 and not args.all_configs:          # under torchrun: headline + C5 sweep + library leg (the per-config
+                continue                                    # summary is a one-GPU table; --all-configs runs it on every rank)
             try:
                 rig.close(); rig.open()                 # the library's buffers are grow-only: every config starts from an empty device
                 rc = measure_config(rig, cid, 1, 1, warm_host_path=False)
