@@ -587,18 +587,39 @@ def c5_sweep(rig: Rig, full: bool = False):
         back = torch.empty(n_out + 64, dtype=torch.uint8).pin_memory()
         out, o2, sha, bst = ctx.decompress_blocks(h_arc.numpy(), aoff, out=back.numpy())         # warm-up (NVRTC, buffers) + check
         ok = bool(np.array_equal(out, np.concatenate(plain))) and set(sha.tolist()) == {1}
-        rig.barrier()
+        rig.torch.cuda.synchronize()
         t0 = time.perf_counter()
         out, o2, sha, bst = ctx.decompress_blocks(h_arc.numpy(), aoff, out=back.numpy())
         rig.torch.cuda.synchronize()
-        t = rig.max_time(time.perf_counter() - t0)
+        t = time.perf_counter() - t0              # this rank's time; main() takes the maximum over the ranks (one collective, outside)
         st = ctx.stats()
         rows.append({"block_bytes": bs, "blocks_per_gpu": 4 * per_method, "methods": ["mid.cfg", lz_method(a0), lzcm_method(a0), bwt_method(a0)],
+                     "seconds": t, "out_bytes_per_gpu": n_out,
                      "decompress_e2e_value": rig.world * n_out / 1e6 / t, "unit": "MB/s", "archive_bytes_per_gpu": int(total_arc),
                      "round_trip_identical": ok, "n_gpus": rig.world,
                      "post_native_blocks_last_group": int(st.post_native_blocks)})
         del h_arc, back
     return rows
+
+
+def reduce_max_list(times, rig):
+    tt = rig.torch.tensor(times, dtype=rig.torch.float64, device=rig.dev)
+    rig.dist.all_reduce(tt, op=rig.dist.ReduceOp.MAX)
+    return [float(x) for x in tt.tolist()]
+
+
+def finish_c5(sweep, err, world, nlegs, full, reduce_max):
+    """One collective for the whole sweep, entered by every rank whatever happened to it (a rank that failed contributes an
+    infinite time): the slowest rank's time per leg decides the whole-job MB/s."""
+    times = reduce_max([sweep[k]["seconds"] if k < len(sweep) else 1e30 for k in range(nlegs)])
+    if err is not None or max(times) >= 1e29:
+        return {"error": err or "a rank failed"}
+    for k, row in enumerate(sweep):
+        row["seconds"] = times[k]
+        row["decompress_e2e_value"] = world * row["out_bytes_per_gpu"] / 1e6 / times[k]
+    return {"workload": "configs[4]: mixed-method archive decompression sweep (mid.cfg / LZ77 stored / LZ77+CM / BWT blocks interleaved)",
+            "sweep": sweep,
+            "note": None if full else "the 16,773,120-byte leg runs with --config C5 (profiles/ holds the last full sweep)"}
 
 
 def library_multi_gpu(rig: Rig, cfg_id: str, B: int):
@@ -714,13 +735,16 @@ def main():
                 del rc
             except Exception as e:                      # a config that fails is reported, it does not take the headline down
                 configs[cid] = {"error": str(e)[:300]}
+        c5_full = args.config == "C5"
+        nlegs = 4 if c5_full else 3
         try:
             rig.close(); rig.open()
-            configs["C5"] = {"workload": "configs[4]: mixed-method archive decompression sweep (mid.cfg / LZ77 stored / LZ77+CM / BWT blocks interleaved)",
-                             "sweep": c5_sweep(rig, full=args.config == "C5"),
-                             "note": None if args.config == "C5" else "the 16,773,120-byte leg runs with --config C5 (profiles/ holds the last full sweep)"}
+            sweep = c5_sweep(rig, full=c5_full)
+            c5_err = None
         except Exception as e:
-            configs["C5"] = {"error": str(e)[:300]}
+            sweep, c5_err = [], str(e)[:300]
+        configs["C5"] = finish_c5(sweep, c5_err, world, nlegs, c5_full,
+                                  (lambda t: reduce_max_list(t, rig)) if world > 1 else (lambda t: t))
     lib_multi = None
     if world > 1 and not args.no_library_multi_gpu:
         try:

@@ -64,3 +64,15 @@ def test_algorithmic_bytes_of_the_survey():
     text, args = z.make_config("x0,0c256,0,255,255")
     h1, _ = z.compile_config(text, args)
     assert abs(bench.algorithmic_bytes(h1, 1 << 20, bench.BLOCK, 0.3, 0) - 66.3) < 0.5
+
+
+def test_c5_sweep_is_reduced_with_one_collective_and_survives_a_failed_rank():
+    import bench
+    rows = [{"seconds": 2.0, "out_bytes_per_gpu": 10 ** 9, "decompress_e2e_value": 0.0}, {"seconds": 4.0, "out_bytes_per_gpu": 10 ** 9, "decompress_e2e_value": 0.0}]
+    slower = lambda t: [max(x, 5.0) for x in t]                   # another rank needed 5 s for every leg
+    out = bench.finish_c5([dict(r) for r in rows], None, 8, 2, False, slower)
+    assert [round(r["decompress_e2e_value"]) for r in out["sweep"]] == [1600, 1600] and out["note"]
+    out = bench.finish_c5([dict(r) for r in rows], None, 1, 2, True, lambda t: t)
+    assert [round(r["decompress_e2e_value"]) for r in out["sweep"]] == [500, 250] and out["note"] is None
+    assert "error" in bench.finish_c5(rows[:1], "out of memory", 2, 2, False, lambda t: t)
+    assert "error" in bench.finish_c5([dict(r) for r in rows], None, 2, 2, False, lambda t: [1e30, 1e30])   # the other rank failed
