@@ -638,6 +638,12 @@ def library_multi_gpu(rig: Rig, cfg_id: str, B: int):
         cfg = CONFIGS[cfg_id]
         bs = cfg["block"]
         how, arg = cfg["how"]
+        try:                                 # the leg pins input + archive + restored bytes of ALL devices on this one host
+            import psutil
+            room = int(0.45 * psutil.virtual_memory().available // (3.4 * bs * world))
+            B = max(1, min(B, room))
+        except Exception:
+            pass
         nb = B * world
         wave = torch.empty(B * bs, dtype=torch.uint8)
         synth.fill(wave.numpy(), cfg["kind"], 0, B, bs)
@@ -659,7 +665,7 @@ def library_multi_gpu(rig: Rig, cfg_id: str, B: int):
             out, o2, sha, bst = ctx.decompress_blocks(arc, ooff, out=back.numpy())
             t0 = time.perf_counter(); out, o2, sha, bst = ctx.decompress_blocks(arc, ooff, out=back.numpy()); td = time.perf_counter() - t0
             ok = bool(np.array_equal(out, host_in.numpy())) and set(sha.tolist()) == {1}
-        res = {"devices": world, "blocks": nb, "compress": {"e2e_value": nb * bs / 1e6 / tc, "unit": "MB/s", "archives_in_block_order": bool(ordered)},
+        res = {"devices": world, "blocks": nb, "blocks_per_device": B, "compress": {"e2e_value": nb * bs / 1e6 / tc, "unit": "MB/s", "archives_in_block_order": bool(ordered)},
                "decompress": {"e2e_value": nb * bs / 1e6 / td, "unit": "MB/s", "round_trip_identical": ok},
                "how": "one zpq_ctx over all devices, one call, host buffers (pinned), wall clock; rank 0 of %d" % world}
         del host_in, host_out, back
