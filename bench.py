@@ -687,6 +687,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the summary of the other configs (C1, C2b, C2c, C3, C4, C5)")
     ap.add_argument("--no-library-multi-gpu", action="store_true")
     ap.add_argument("--all-configs", action="store_true", help="N > 1: also run the C1 .. C4 summary on every rank")
+    ap.add_argument("--configs", default="C1,C2a,C2b,C2c,C3,C4,C5", help="which configs the summary holds (comma separated)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -729,7 +730,7 @@ def main():
     configs = {}
     if not args.no_configs:
         for cid in ("C1", "C2a", "C2b", "C2c", "C3", "C4"):
-            if cid == head_id or args.config == "C5":       # --config C5: the headline line plus the FULL sweep, nothing else
+            if cid == head_id or args.config == "C5" or cid not in args.configs.split(","):   # --config C5: the headline line plus the FULL sweep, nothing else
                 continue
             if world > 1 and not args.all_configs:          # under torchrun: headline + C5 sweep + library leg (the per-config
                 continue                                    # summary is a one-GPU table; --all-configs runs it on every rank)
@@ -741,16 +742,17 @@ def main():
                 del rc
             except Exception as e:                      # a config that fails is reported, it does not take the headline down
                 configs[cid] = {"error": str(e)[:300]}
-        c5_full = args.config == "C5"
-        nlegs = 4 if c5_full else 3
-        try:
-            rig.close(); rig.open()
-            sweep = c5_sweep(rig, full=c5_full)
-            c5_err = None
-        except Exception as e:
-            sweep, c5_err = [], str(e)[:300]
-        configs["C5"] = finish_c5(sweep, c5_err, world, nlegs, c5_full,
-                                  (lambda t: reduce_max_list(t, rig)) if world > 1 else (lambda t: t))
+        if "C5" in args.configs.split(",") or args.config == "C5":
+            c5_full = args.config == "C5"
+            nlegs = 4 if c5_full else 3
+            try:
+                rig.close(); rig.open()
+                sweep = c5_sweep(rig, full=c5_full)
+                c5_err = None
+            except Exception as e:
+                sweep, c5_err = [], str(e)[:300]
+            configs["C5"] = finish_c5(sweep, c5_err, world, nlegs, c5_full,
+                                      (lambda t: reduce_max_list(t, rig)) if world > 1 else (lambda t: t))
     lib_multi = None
     if world > 1 and not args.no_library_multi_gpu:
         try:
