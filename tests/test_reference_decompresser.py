@@ -128,3 +128,25 @@ def test_reference_decoder_restores_multi_segment_blocks(ref, level):
     assert marks == [b"\x01" + po.sha1(data[cuts[k]:cuts[k + 1]]) for k in range(len(cuts) - 1)]
     got, st = po.decompress(arc)
     assert got == data and st == [1] * (len(cuts) - 1)
+
+
+@pytest.mark.parametrize("method", ["x0,4c0,0,255", "x0,2,12,0,7,21,1c0,0,255", "x0,1,4,0,7,21,1", "x0,5,4,0,3,19"])
+def test_reference_decoder_restarts_the_pcomp_programs_at_every_segment_end(ref, method):
+    """The native post-processors restore every segment on its own: makeConfig's programs reset their registers in their
+    end-of-segment branch (LibZPAQ.cs:465, :599, :805-812).  The reference's Decompresser / PostProcessor / ZPAQL text says the same:
+    a block whose segments carry independently transformed data decodes to the concatenation of the originals."""
+    from oracle import frontend as fe
+    text, args = fe.make_config(method)
+    hdr, pcomp = fe.compile_config(text, args)[:2]
+    data = _data(120, 24000)
+    cuts = [0, 5000, 5000, 5001, 12000, 24000]
+    parts = [data[cuts[k]:cuts[k + 1]] for k in range(len(cuts) - 1)]
+    stream = [po.preprocess(p, list(args)) for p in parts]
+    scuts = [0]
+    for x in stream:
+        scuts.append(scuts[-1] + len(x))
+    arc = po.compress_segments(bytes(hdr), bytes(pcomp), b"".join(stream), scuts, dosha1=False)
+    n, out, marks = _ref_decompress(ref, arc, len(data) + 64)
+    assert n == len(data) and out == data
+    got, _ = po.decompress(arc, cap=1 << 20)
+    assert got == data
