@@ -173,3 +173,80 @@ def restore(kind: int, e8: int, param: int, ph: int, pm: int, data: bytes):
     if e8:
         un_e8e9(M)
     return OK, bytes(M)
+
+
+def bwt_walk_split(T, idx: int, size: int, data: bytes, max_split: int = 2048):
+    """The list traversal of k_post_bwt as the kernel does it: sub-lists start at idx and at every other multiple of `stride`, each
+    ends at the next multiple (or at position 0); one pass measures them, the heads are ranked along the chain from idx, a second
+    pass emits.  Returns the emitted bytes."""
+    stride = 64
+    while (size + stride - 1) // stride > max_split:
+        stride <<= 1
+    nsplit = (size + stride - 1) // stride
+    slen, send, soff = [0] * nsplit, [0] * nsplit, [None] * nsplit
+    for j in range(nsplit):
+        p, n = (j * stride if j else idx), 0
+        if p != 0:
+            while True:
+                p = T[p]
+                n += 1
+                if (p & (stride - 1)) == 0 or n > size:
+                    break
+        slen[j] = n
+        send[j] = p // stride if (p & (stride - 1)) == 0 else 0
+    cur = off = 0
+    for _ in range(nsplit + 1):
+        if soff[cur] is not None:
+            break
+        soff[cur] = off
+        off += slen[cur]
+        e = send[cur]
+        if e == 0 or e >= nsplit:
+            break
+        cur = e
+    out = bytearray(off)
+    for j in range(nsplit):
+        if soff[j] is None:
+            continue
+        p = j * stride if j else idx
+        for k in range(slen[j]):
+            p = T[p]
+            out[soff[j] + k] = data[p]
+    return bytes(out)
+
+
+def bwt_list(data: bytes, size: int, idx: int):
+    cnt = [0] * 256
+    for b in range(size):
+        cnt[data[b]] += 1
+    C, run = [0] * 256, 1
+    for v in range(256):
+        C[v] = run
+        run += cnt[v]
+    T = [0] * (size + 1)
+    for b in range(size):
+        if b != idx:
+            T[C[data[b]]] = b
+            C[data[b]] += 1
+    return T
+
+
+def gap_hist_chunked(data: bytes, bins: int = 4096):
+    """k_gap_hist: per 4096-position chunk, every position walks back through the chunk and the 4095 bytes in front of it."""
+    n = len(data)
+    gap = [0] * bins
+    for c0 in range(0, n, bins):
+        lo = c0 - bins if c0 >= bins else 0
+        hi = min(n, c0 + bins)
+        buf = data[lo:hi]
+        for i in range(c0, hi):
+            at, v = i - lo, data[i]
+            reach = min(bins - 1, i)
+            k = 1
+            while k <= reach and buf[at - k] != v:
+                k += 1
+            if k <= reach:
+                gap[k] += 1
+            elif 0 < i < bins:
+                gap[i] += 1
+    return gap

@@ -91,3 +91,58 @@ def test_native_algorithms_write_what_the_program_writes(oracle, zlib_, method):
             except mp.TimeoutError:
                 pytest.fail("the program did not finish on a stream the native form accepted (%d bytes)" % len(s))
             assert want is not None and want == out, (method, len(s), len(out), None if want is None else len(want))
+
+
+def test_bwt_sub_list_walk_equals_the_sequential_walk(oracle):
+    """The parallel list ranking of k_post_bwt (sub-lists between multiples of a stride) emits what the sequential traversal of the
+    program emits -- for real BWT streams of many sizes (smaller than one stride, start index a multiple of the stride, ...) and
+    for damaged ones whose list is shorter than the block."""
+    from native_post_model import bwt_list, bwt_segment, bwt_walk_split
+    from tools import synth
+    rng = np.random.default_rng(99)
+    args = [0, 3, 0, 0, 0, 0, 0, 0, 0]
+    sizes = [1, 2, 5, 63, 64, 65, 127, 128, 129, 1000, 4096, 9000, 70000]
+    for t, n in enumerate(sizes):
+        src = synth.blocks("text" if t % 2 else "mixed", 5000 + t, 1, max(n, 16)).tobytes()[:n]
+        good = oracle.preprocess(src, args)
+        streams = [good]
+        for _ in range(3):
+            bad = bytearray(good)
+            if len(bad) > 6:
+                bad[int(rng.integers(0, len(bad) - 4))] ^= 1 << int(rng.integers(0, 8))
+            streams.append(bytes(bad))
+        for s in streams:
+            rc, want = bwt_segment(s, 24)
+            if rc != OK:
+                continue
+            size = len(s) - 4
+            idx = int.from_bytes(s[size:size + 4], "little")
+            for max_split in (2048, 4, 1):
+                assert bwt_walk_split(bwt_list(s, size, idx), idx, size, s, max_split) == bytes(want), (n, max_split)
+        assert bwt_segment(good, 24)[1] == src
+    # a start index that is a multiple of the stride: no sub-list ends there (idx is not in the image of the list)
+    s = oracle.preprocess(bytes(range(256)) * 2, args)
+    size = len(s) - 4
+    for idx in (0, 64, 128, 448):
+        t = s[:size] + idx.to_bytes(4, "little")
+        rc, want = bwt_segment(t, 24)
+        assert rc == OK and bwt_walk_split(bwt_list(t, size, idx), idx, size, t) == bytes(want)
+
+
+def test_chunked_gap_histogram_equals_the_reference_loop(zlib_):
+    """k_gap_hist counts per 4096-position chunk what LibZPAQ.cs:242-258 counts in one pass over the block (checked through the
+    method string the host front end derives from either: expand_method runs the reference's loop)."""
+    from native_post_model import gap_hist_chunked
+    from tools import synth
+    rng = np.random.default_rng(5)
+    cases = [b"", b"a", b"abcabcabc" * 50, bytes(range(37)) * 400, bytes(rng.integers(0, 256, 9000, dtype=np.uint8)),
+             synth.blocks("mixed", 77, 1, 20000).tobytes(), b"\\x00" * 5000 + b"\\x01" + b"\\x00" * 5000, bytes(rng.integers(0, 3, 13000, dtype=np.uint8))]
+    for d in cases:
+        ref = [0] * 4096
+        last = [0] * 256
+        for i, v in enumerate(d):
+            k = i - last[v]
+            if 0 < k < 4096:
+                ref[k] += 1
+            last[v] = i
+        assert gap_hist_chunked(d) == ref, len(d)
