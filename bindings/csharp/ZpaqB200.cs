@@ -41,6 +41,7 @@ namespace ZPAQSharp
         [DllImport(Lib)] public static extern long zpq_device_state_bytes(byte* hdr, ulong hdrLen, int forDecode);
         [DllImport(Lib)] public static extern long zpq_device_state_bytes_for(byte* hdr, ulong hdrLen, int forDecode, ulong maxBlockBytes);
         [DllImport(Lib)] public static extern long zpq_post_kind(int ph, int pm, byte* pcomp, ulong len);
+        [DllImport(Lib)] public static extern long zpq_specialize_pcomp(int ph, int pm, byte* pcomp, ulong len, byte* source, ulong sourceCap, byte* log, ulong logCap);
         [DllImport(Lib)] public static extern int zpq_encoder_plan(byte* hdr, ulong hdrLen, uint smemBytes, uint blocksPerSm, int* out8);
     }
 
